@@ -1,0 +1,776 @@
+// abi.cu — extern "C" entry points of libbsm_b200.so (see include/bsm_b200.h).
+// Front-ends lower the three reference storage types to contributions, pack.cpp builds the plans,
+// this file owns the device copies and launches the kernels. No CPU fallback: every compute entry
+// point needs a CUDA device and fails with BSM_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "plan.h"
+
+using namespace bsm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(BSM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));   \
+    } while (0)
+
+template <class U>
+struct DevBuf {
+    U *p = nullptr;
+    int64_t n = 0;
+    int upload(const std::vector<U> &h) {
+        n = (int64_t)h.size();
+        if (n == 0) {
+            // keep a valid non-null pointer so kernels can form addresses
+            CUDA_TRY(cudaMalloc((void **)&p, 16));
+            return 0;
+        }
+        CUDA_TRY(cudaMalloc((void **)&p, (size_t)n * sizeof(U)));
+        CUDA_TRY(cudaMemcpy(p, h.data(), (size_t)n * sizeof(U), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
+};
+
+struct DevPlan {
+    DevBuf<bsm_contrib> contrib;
+    DevBuf<bsm_slice> slices;
+    DevBuf<int32_t> gather_rows;
+    DevBuf<int64_t> gather_ptr, gather_pos;
+    void release() {
+        contrib.release();
+        slices.release();
+        gather_rows.release();
+        gather_ptr.release();
+        gather_pos.release();
+    }
+};
+
+}  // namespace
+
+struct bsm_matrix {
+    HostMatrix H;  // block sources are cleared after upload; tables stay for export
+    int device = 0;
+    int variant = BSM_VARIANT_AUTO;
+    void *arena = nullptr;
+    DevBuf<int32_t> set_len, set_start, pool;
+    DevBuf<int64_t> set_pool_off;
+    DevPlan plan[2];
+    // host-pointer path
+    std::mutex host_mu;
+    void *hx = nullptr, *hy = nullptr;
+    int64_t hx_bytes = 0, hy_bytes = 0;
+    cudaStream_t host_stream = nullptr;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+        if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int resolve_device(const bsm_options *opt, int *dev) {
+    if (opt && opt->device == BSM_DEVICE_NONE) {
+        *dev = BSM_DEVICE_NONE;
+        return 0;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(BSM_ERR_CUDA, std::string("no CUDA device available (libbsm_b200 has no CPU fallback): ") +
+                                      cudaGetErrorString(e));
+    int d = opt ? opt->device : -1;
+    if (d < 0) CUDA_TRY(cudaGetDevice(&d));
+    if (d >= count) return fail(BSM_ERR_ARG, "device ordinal out of range");
+    *dev = d;
+    return 0;
+}
+
+// Copies every block into the device arena through two pinned staging buffers.
+int upload_arena(bsm_matrix *A) {
+    HostMatrix &H = A->H;
+    const int64_t s = dtype_size(H.dtype);
+    CUDA_TRY(cudaMalloc(&A->arena, (size_t)H.arena_elems * s));
+    CUDA_TRY(cudaMemset(A->arena, 0, (size_t)H.arena_elems * s));
+    const int64_t stage_bytes = 64ll << 20;
+    unsigned char *stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2];
+    cudaStream_t st;
+    CUDA_TRY(cudaStreamCreate(&st));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaMallocHost((void **)&stage[i], (size_t)stage_bytes));
+        CUDA_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+    }
+    int cur = 0;
+    int64_t fill = 0;        // bytes used in stage[cur]
+    int64_t dst_off = -1;    // arena byte offset the staged run starts at
+    auto flush = [&]() -> int {
+        if (fill == 0) return 0;
+        CUDA_TRY(cudaMemcpyAsync((unsigned char *)A->arena + dst_off, stage[cur], (size_t)fill,
+                                 cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(done[cur], st));
+        cur ^= 1;
+        CUDA_TRY(cudaEventSynchronize(done[cur]));
+        fill = 0;
+        dst_off = -1;
+        return 0;
+    };
+    for (size_t b = 0; b < H.blocks.size(); ++b) {
+        const BlockSrc &src = H.blocks[b];
+        const int64_t bytes = (int64_t)src.m * src.n * s;
+        const int64_t boff = H.block_off[b] * s;
+        int64_t done_b = 0;
+        while (done_b < bytes) {
+            // staged runs must be contiguous in the arena: the gap between blocks is alignment
+            // padding (already zero), so a run simply continues at boff + done_b
+            if (fill > 0 && dst_off + fill != boff + done_b) {
+                const int64_t gap = boff + done_b - (dst_off + fill);
+                if (gap > 0 && fill + gap < stage_bytes) {
+                    std::memset(stage[cur] + fill, 0, (size_t)gap);
+                    fill += gap;
+                } else if (int rc = flush()) {
+                    return rc;
+                }
+            }
+            if (fill == 0) dst_off = boff + done_b;
+            const int64_t take = std::min(bytes - done_b, stage_bytes - fill);
+            if (!src.transposed) {
+                std::memcpy(stage[cur] + fill, (const unsigned char *)src.host + done_b, (size_t)take);
+            } else {
+                // arena block is m x n (ld m); host parent is n x m (ld n): A[i,j] = Parent[j,i]
+                const int64_t e0 = done_b / s, e1 = (done_b + take) / s;
+                for (int64_t e = e0; e < e1; ++e) {
+                    const int64_t i = e % src.m, j = e / src.m;
+                    std::memcpy(stage[cur] + fill + (e - e0) * s,
+                                (const unsigned char *)src.host + (i * src.n + j) * s, (size_t)s);
+                }
+            }
+            fill += take;
+            done_b += take;
+            if (fill == stage_bytes)
+                if (int rc = flush()) return rc;
+        }
+    }
+    if (int rc = flush()) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < 2; ++i) {
+        cudaFreeHost(stage[i]);
+        cudaEventDestroy(done[i]);
+    }
+    cudaStreamDestroy(st);
+    return 0;
+}
+
+int upload_tables(bsm_matrix *A) {
+    HostMatrix &H = A->H;
+    if (int rc = A->set_len.upload(H.sets.len)) return rc;
+    if (int rc = A->set_start.upload(H.sets.start)) return rc;
+    if (int rc = A->set_pool_off.upload(H.sets.pool_off)) return rc;
+    if (int rc = A->pool.upload(H.sets.pool)) return rc;
+    for (int p = 0; p < 2; ++p) {
+        if (int rc = A->plan[p].contrib.upload(H.plan[p].contrib)) return rc;
+        if (int rc = A->plan[p].slices.upload(H.plan[p].slices)) return rc;
+        if (int rc = A->plan[p].gather_rows.upload(H.plan[p].gather_rows)) return rc;
+        if (int rc = A->plan[p].gather_ptr.upload(H.plan[p].gather_ptr)) return rc;
+        if (int rc = A->plan[p].gather_pos.upload(H.plan[p].gather_pos)) return rc;
+    }
+    return 0;
+}
+
+// Shared tail of the three create functions.
+int finish_create(bsm_matrix *A, const std::vector<ContribIR> ir[2], const bsm_options *opt,
+                  bsm_handle *out) {
+    HostMatrix &H = A->H;
+    if (H.nrows >= (1ll << 31) || H.ncols >= (1ll << 31)) {
+        delete A;
+        return fail(BSM_ERR_UNSUPPORTED, "matrix dimension does not fit Int32 device indices");
+    }
+    layout_arena(H);
+    PlanParams pp[2];
+    if (opt) {
+        pp[0].own_lo = opt->own_row_lo;
+        pp[0].own_hi = opt->own_row_hi;
+        pp[1].own_lo = opt->own_col_lo;
+        pp[1].own_hi = opt->own_col_hi;
+        A->variant = opt->variant;
+    }
+    std::string err = build_plan(H, ir[0], H.nrows, H.ncols, pp[0], H.plan[0]);
+    if (err.empty()) err = build_plan(H, ir[1], H.ncols, H.nrows, pp[1], H.plan[1]);
+    if (!err.empty()) {
+        delete A;
+        return fail(BSM_ERR_ARG, err);
+    }
+    if (A->device == BSM_DEVICE_NONE) {  // host-only handle: tables only
+        for (auto &b : H.blocks) b.host = nullptr;
+        *out = A;
+        return 0;
+    }
+    DeviceGuard g(A->device);
+    if (!g.ok) {
+        delete A;
+        return fail(BSM_ERR_CUDA, "cudaSetDevice failed");
+    }
+    int rc = upload_arena(A);
+    if (rc == 0) rc = upload_tables(A);
+    if (rc != 0) {
+        std::string keep = g_err;
+        bsm_destroy(A);
+        g_err = keep;
+        return rc;
+    }
+    for (auto &b : H.blocks) b.host = nullptr;  // host blocks are not referenced after create
+    *out = A;
+    return 0;
+}
+
+template <class T>
+int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int beta_is_false,
+               const T *x, int64_t ldx, T *y, int64_t ldy, int64_t nrhs, cudaStream_t st) {
+    const int p = (op == BSM_OP_N) ? 0 : 1;
+    const HostPlan &HP = A->H.plan[p];
+    const DevPlan &DP = A->plan[p];
+    T *scratch = nullptr;
+    if (HP.scratch_elems > 0)
+        CUDA_TRY(cudaMallocAsync((void **)&scratch, (size_t)HP.scratch_elems * sizeof(T), st));
+    constexpr int VMAX = 16 / (int)sizeof(T);
+    for (int64_t j = 0; j < nrhs; ++j) {
+        MulArgs<T> a;
+        a.arena = (const T *)A->arena;
+        a.contrib = DP.contrib.p;
+        a.slices = DP.slices.p;
+        a.set_len = A->set_len.p;
+        a.set_start = A->set_start.p;
+        a.set_pool_off = A->set_pool_off.p;
+        a.pool = A->pool.p;
+        a.x = x + j * ldx;
+        a.y = y + j * ldy;
+        a.scratch = scratch;
+        std::memcpy(&a.alpha, alpha, sizeof(T));
+        if (beta_is_false)
+            std::memset(&a.beta, 0, sizeof(T));
+        else
+            std::memcpy(&a.beta, beta, sizeof(T));
+        a.nslices = (int32_t)HP.slices.size();
+        a.beta_false = beta_is_false ? 1 : 0;
+        a.conj = (op == BSM_OP_C && sizeof(T) == 16) ? 1 : 0;
+        if (a.nslices > 0) {
+            gather_gemv_kernel<T, VMAX><<<a.nslices, kThreads, 0, st>>>(a);
+            CUDA_TRY(cudaGetLastError());
+        }
+        const int64_t ng = (int64_t)HP.gather_rows.size();
+        if (ng > 0) {
+            FinalizeArgs<T> f;
+            f.rows = DP.gather_rows.p;
+            f.ptr = DP.gather_ptr.p;
+            f.pos = DP.gather_pos.p;
+            f.scratch = scratch;
+            f.y = y + j * ldy;
+            f.alpha = a.alpha;
+            f.beta = a.beta;
+            f.n = ng;
+            f.beta_false = a.beta_false;
+            gather_finalize_kernel<T><<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(f);
+            CUDA_TRY(cudaGetLastError());
+        }
+    }
+    if (scratch) CUDA_TRY(cudaFreeAsync(scratch, st));
+    return 0;
+}
+
+int check_handle(bsm_handle h) {
+    if (!h) return fail(BSM_ERR_ARG, "null handle");
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================= C ABI
+
+extern "C" {
+
+const char *bsm_last_error(void) { return g_err.c_str(); }
+const char *bsm_version(void) { return "bsm_b200 0.1.0 (sm_100a)"; }
+
+void bsm_default_options(bsm_options *opt) {
+    if (!opt) return;
+    std::memset(opt, 0, sizeof(*opt));
+    opt->device = -1;
+    opt->variant = BSM_VARIANT_AUTO;
+    opt->own_row_lo = 0;
+    opt->own_row_hi = -1;
+    opt->own_col_lo = 0;
+    opt->own_col_hi = -1;
+}
+
+int bsm_create_blocksparse(int dtype, int64_t nrows, int64_t ncols, int64_t nb,
+                           const void *const *blocks, const int64_t *m, const int64_t *n,
+                           const int64_t *rowidx, const int64_t *rowptr, const int64_t *colidx,
+                           const int64_t *colptr, const bsm_options *opt, bsm_handle *out) {
+    if (!out) return fail(BSM_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (dtype < 0 || dtype > 2) return fail(BSM_ERR_ARG, "bad dtype");
+    if (nrows < 0 || ncols < 0 || nb < 0) return fail(BSM_ERR_ARG, "negative size");
+    if (nb > 0 && (!blocks || !m || !n || !rowidx || !rowptr || !colidx || !colptr))
+        return fail(BSM_ERR_ARG, "null array");
+    int dev = 0;
+    if (int rc = resolve_device(opt, &dev)) return rc;
+    bsm_matrix *A = new (std::nothrow) bsm_matrix();
+    if (!A) return fail(BSM_ERR_ALLOC, "out of host memory");
+    A->device = dev;
+    HostMatrix &H = A->H;
+    H.dtype = dtype;
+    H.kind = BSM_KIND_BLOCKSPARSE;
+    H.nrows = nrows;
+    H.ncols = ncols;
+    std::vector<ContribIR> ir[2];
+    for (int64_t b = 0; b < nb; ++b) {
+        if (m[b] < 0 || n[b] < 0 || rowptr[b + 1] - rowptr[b] != m[b] || colptr[b + 1] - colptr[b] != n[b] ||
+            (m[b] * n[b] > 0 && !blocks[b])) {
+            delete A;
+            return fail(BSM_ERR_ARG, "block " + std::to_string(b) + ": size does not match its index vectors");
+        }
+        const int32_t rs = H.sets.add_vector(rowidx + rowptr[b], m[b], nrows);
+        const int32_t cs = H.sets.add_vector(colidx + colptr[b], n[b], ncols);
+        if (rs < 0 || cs < 0) {
+            delete A;
+            return fail(BSM_ERR_ARG, "block " + std::to_string(b) + ": index out of range");
+        }
+        H.blocks.push_back(BlockSrc{blocks[b], (int32_t)m[b], (int32_t)n[b], false});
+        H.nnz += m[b] * n[b];
+        // y[R_b] += op(B_b) x[C_b]   (/root/reference/src/blockmatrix.jl:236-242)
+        ir[0].push_back(ContribIR{(int32_t)b, 0, rs, cs, (int32_t)m[b]});
+        // wrappers swap the index vectors (/root/reference/src/symmetricblockmatrix.jl:345-365)
+        ir[1].push_back(ContribIR{(int32_t)b, 1, cs, rs, (int32_t)n[b]});
+    }
+    return finish_create(A, ir, opt, out);
+}
+
+int bsm_create_symmetric(int dtype, int64_t nrows, int64_t ncols, int64_t ndiag,
+                         const void *const *diag, const int64_t *dsize, const int64_t *didx,
+                         const int64_t *dptr, int64_t noff, const void *const *off,
+                         const int64_t *om, const int64_t *on, const int64_t *rowidx,
+                         const int64_t *rowptr, const int64_t *colidx, const int64_t *colptr,
+                         const bsm_options *opt, bsm_handle *out) {
+    if (!out) return fail(BSM_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (dtype < 0 || dtype > 2) return fail(BSM_ERR_ARG, "bad dtype");
+    if (nrows < 0 || ncols < 0 || ndiag < 0 || noff < 0) return fail(BSM_ERR_ARG, "negative size");
+    if (nrows != ncols) return fail(BSM_ERR_ARG, "a SymmetricBlockMatrix must be square");
+    if (ndiag > 0 && (!diag || !dsize || !didx || !dptr)) return fail(BSM_ERR_ARG, "null diagonal array");
+    if (noff > 0 && (!off || !om || !on || !rowidx || !rowptr || !colidx || !colptr))
+        return fail(BSM_ERR_ARG, "null off-diagonal array");
+    int dev = 0;
+    if (int rc = resolve_device(opt, &dev)) return rc;
+    bsm_matrix *A = new (std::nothrow) bsm_matrix();
+    if (!A) return fail(BSM_ERR_ALLOC, "out of host memory");
+    A->device = dev;
+    HostMatrix &H = A->H;
+    H.dtype = dtype;
+    H.kind = BSM_KIND_SYMMETRIC;
+    H.nrows = nrows;
+    H.ncols = ncols;
+    std::vector<ContribIR> ir[2];
+    // diagonal sweep (/root/reference/src/symmetricblockmatrix.jl:420-432); emitted first so the
+    // leaf segments claim their rows and are written directly
+    for (int64_t d = 0; d < ndiag; ++d) {
+        if (dsize[d] < 0 || dptr[d + 1] - dptr[d] != dsize[d] || (dsize[d] > 0 && !diag[d])) {
+            delete A;
+            return fail(BSM_ERR_ARG, "diagonal block " + std::to_string(d) + ": size mismatch");
+        }
+        const int32_t ds = H.sets.add_vector(didx + dptr[d], dsize[d], nrows);
+        if (ds < 0) {
+            delete A;
+            return fail(BSM_ERR_ARG, "diagonal block " + std::to_string(d) + ": index out of range");
+        }
+        H.blocks.push_back(BlockSrc{diag[d], (int32_t)dsize[d], (int32_t)dsize[d], false});
+        H.nnz += dsize[d] * dsize[d];
+        ir[0].push_back(ContribIR{(int32_t)d, 0, ds, ds, (int32_t)dsize[d]});
+        ir[1].push_back(ContribIR{(int32_t)d, 1, ds, ds, (int32_t)dsize[d]});  // transpose(D)/adjoint(D), :225-237
+    }
+    std::vector<int32_t> rs((size_t)noff), cs((size_t)noff);
+    for (int64_t b = 0; b < noff; ++b) {
+        if (om[b] < 0 || on[b] < 0 || rowptr[b + 1] - rowptr[b] != om[b] || colptr[b + 1] - colptr[b] != on[b] ||
+            (om[b] * on[b] > 0 && !off[b])) {
+            delete A;
+            return fail(BSM_ERR_ARG, "off-diagonal block " + std::to_string(b) + ": size mismatch");
+        }
+        rs[b] = H.sets.add_vector(rowidx + rowptr[b], om[b], nrows);
+        cs[b] = H.sets.add_vector(colidx + colptr[b], on[b], ncols);
+        if (rs[b] < 0 || cs[b] < 0) {
+            delete A;
+            return fail(BSM_ERR_ARG, "off-diagonal block " + std::to_string(b) + ": index out of range");
+        }
+        H.blocks.push_back(BlockSrc{off[b], (int32_t)om[b], (int32_t)on[b], false});
+        H.nnz += 2 * om[b] * on[b];
+    }
+    // y[R_b] += O_b x[C_b]: sweep 1 of A (:394-405) and sweep 2 of the wrappers (:407-418, where
+    // transpose(op(O_b)) is O_b or conj(O_b))
+    for (int64_t b = 0; b < noff; ++b) {
+        const int32_t blk = (int32_t)(ndiag + b);
+        ir[0].push_back(ContribIR{blk, 0, rs[b], cs[b], (int32_t)om[b]});
+        ir[1].push_back(ContribIR{blk, 0, rs[b], cs[b], (int32_t)om[b]});
+    }
+    // y[C_b] += transpose(O_b) x[R_b]: sweep 2 of A and sweep 1 of the wrappers
+    for (int64_t b = 0; b < noff; ++b) {
+        const int32_t blk = (int32_t)(ndiag + b);
+        ir[0].push_back(ContribIR{blk, 1, cs[b], rs[b], (int32_t)on[b]});
+        ir[1].push_back(ContribIR{blk, 1, cs[b], rs[b], (int32_t)on[b]});
+    }
+    return finish_create(A, ir, opt, out);
+}
+
+int bsm_create_vbcrs(int dtype, int64_t nrows, int64_t ncols, int64_t nbrows, int64_t nb,
+                     const int64_t *rowptr, const int64_t *colstart, const int64_t *rowstart,
+                     const void *const *blocks, const int64_t *m, const int64_t *n,
+                     const uint8_t *is_transposed, const bsm_options *opt, bsm_handle *out) {
+    if (!out) return fail(BSM_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (dtype < 0 || dtype > 2) return fail(BSM_ERR_ARG, "bad dtype");
+    if (nrows < 0 || ncols < 0 || nbrows < 0 || nb < 0) return fail(BSM_ERR_ARG, "negative size");
+    if (!rowptr) return fail(BSM_ERR_ARG, "rowptr is null");
+    if (nb > 0 && (!colstart || !rowstart || !blocks || !m || !n)) return fail(BSM_ERR_ARG, "null array");
+    if (rowptr[0] != 1 || rowptr[nbrows] != nb + 1) return fail(BSM_ERR_ARG, "rowptr must be 1-based with sentinel nb+1");
+    int dev = 0;
+    if (int rc = resolve_device(opt, &dev)) return rc;
+    bsm_matrix *A = new (std::nothrow) bsm_matrix();
+    if (!A) return fail(BSM_ERR_ALLOC, "out of host memory");
+    A->device = dev;
+    HostMatrix &H = A->H;
+    H.dtype = dtype;
+    H.kind = BSM_KIND_VBCRS;
+    H.nrows = nrows;
+    H.ncols = ncols;
+    // segment lengths: a block row is keyed by its start row only and the height is taken per block
+    // (/root/reference/src/vbcrs.jl:108, :280-282) → the row segment is as long as its tallest
+    // block; likewise column segments are keyed by the start column
+    std::vector<int32_t> brow_of((size_t)nb);
+    std::vector<int64_t> rowlen((size_t)nbrows, 0);
+    std::unordered_map<int64_t, int64_t> collen;
+    for (int64_t r = 0; r < nbrows; ++r) {
+        if (rowptr[r + 1] < rowptr[r]) {
+            delete A;
+            return fail(BSM_ERR_ARG, "rowptr must be non-decreasing");
+        }
+        for (int64_t b = rowptr[r] - 1; b < rowptr[r + 1] - 1; ++b) {
+            if (m[b] < 0 || n[b] < 0 || (m[b] * n[b] > 0 && !blocks[b]) || rowstart[r] < 1 ||
+                rowstart[r] + m[b] - 1 > nrows || colstart[b] < 1 || colstart[b] + n[b] - 1 > ncols) {
+                delete A;
+                return fail(BSM_ERR_ARG, "block " + std::to_string(b) + ": range outside the matrix");
+            }
+            brow_of[b] = (int32_t)r;
+            rowlen[r] = std::max(rowlen[r], m[b]);
+            auto it = collen.find(colstart[b]);
+            if (it == collen.end())
+                collen[colstart[b]] = n[b];
+            else
+                it->second = std::max(it->second, n[b]);
+        }
+    }
+    // block rows with the same start row (legal, if unusual) share one segment
+    std::unordered_map<int64_t, int64_t> rowlen_by_start;
+    for (int64_t r = 0; r < nbrows; ++r) {
+        auto it = rowlen_by_start.find(rowstart[r]);
+        if (it == rowlen_by_start.end())
+            rowlen_by_start[rowstart[r]] = rowlen[r];
+        else
+            it->second = std::max(it->second, rowlen[r]);
+    }
+    std::vector<ContribIR> ir[2];
+    for (int64_t b = 0; b < nb; ++b) {
+        const int64_t r = brow_of[b];
+        const bool tr = is_transposed && is_transposed[b];
+        H.blocks.push_back(BlockSrc{blocks[b], (int32_t)m[b], (int32_t)n[b], tr});
+        H.nnz += m[b] * n[b];
+        const int32_t out_rows = H.sets.add_range(rowstart[r] - 1, rowlen_by_start[rowstart[r]]);
+        const int32_t in_cols = H.sets.add_range(colstart[b] - 1, n[b]);
+        const int32_t out_cols = H.sets.add_range(colstart[b] - 1, collen[colstart[b]]);
+        const int32_t in_rows = H.sets.add_range(rowstart[r] - 1, m[b]);
+        ir[0].push_back(ContribIR{(int32_t)b, 0, out_rows, in_cols, (int32_t)m[b]});   // src/vbcrs.jl:277-284
+        ir[1].push_back(ContribIR{(int32_t)b, 1, out_cols, in_rows, (int32_t)n[b]});   // src/vbcrs.jl:315-326
+    }
+    return finish_create(A, ir, opt, out);
+}
+
+int bsm_destroy(bsm_handle h) {
+    if (!h) return 0;
+    if (h->device == BSM_DEVICE_NONE) {
+        delete h;
+        return 0;
+    }
+    DeviceGuard g(h->device);
+    if (h->arena) cudaFree(h->arena);
+    h->set_len.release();
+    h->set_start.release();
+    h->set_pool_off.release();
+    h->pool.release();
+    h->plan[0].release();
+    h->plan[1].release();
+    if (h->hx) cudaFree(h->hx);
+    if (h->hy) cudaFree(h->hy);
+    if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    delete h;
+    return 0;
+}
+
+int bsm_set_variant(bsm_handle h, int variant) {
+    if (int rc = check_handle(h)) return rc;
+    if (variant < BSM_VARIANT_AUTO || variant > BSM_VARIANT_COLOR) return fail(BSM_ERR_ARG, "bad variant");
+    h->variant = variant;
+    return 0;
+}
+
+int bsm_mul(bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
+            const void *x_dev, int64_t ldx, void *y_dev, int64_t ldy, int64_t nrhs, void *stream) {
+    if (int rc = check_handle(h)) return rc;
+    if (op < BSM_OP_N || op > BSM_OP_C) return fail(BSM_ERR_ARG, "bad op");
+    if (!alpha || (!beta && !beta_is_false)) return fail(BSM_ERR_ARG, "alpha/beta is null");
+    if (nrhs < 0) return fail(BSM_ERR_ARG, "negative nrhs");
+    if (nrhs == 0) return 0;
+    if (!x_dev || !y_dev) return fail(BSM_ERR_ARG, "x or y is null");
+    if (h->device == BSM_DEVICE_NONE) return fail(BSM_ERR_CUDA, "host-only handle: no device, and there is no CPU fallback");
+    const int64_t nout = (op == BSM_OP_N) ? h->H.nrows : h->H.ncols;
+    const int64_t nin = (op == BSM_OP_N) ? h->H.ncols : h->H.nrows;
+    if (nrhs > 1 && (ldx < nin || ldy < nout)) return fail(BSM_ERR_ARG, "leading dimension too small");
+    DeviceGuard g(h->device);
+    if (!g.ok) return fail(BSM_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (h->H.dtype) {
+    case BSM_F32:
+        return launch_mul<float>(h, op, alpha, beta, beta_is_false, (const float *)x_dev, ldx,
+                                 (float *)y_dev, ldy, nrhs, st);
+    case BSM_F64:
+        return launch_mul<double>(h, op, alpha, beta, beta_is_false, (const double *)x_dev, ldx,
+                                  (double *)y_dev, ldy, nrhs, st);
+    default:
+        return launch_mul<cplx>(h, op, alpha, beta, beta_is_false, (const cplx *)x_dev, ldx,
+                                (cplx *)y_dev, ldy, nrhs, st);
+    }
+}
+
+int bsm_mul_host(bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
+                 const void *x_host, int64_t ldx, void *y_host, int64_t ldy, int64_t nrhs) {
+    if (int rc = check_handle(h)) return rc;
+    if (op < BSM_OP_N || op > BSM_OP_C) return fail(BSM_ERR_ARG, "bad op");
+    if (nrhs < 0) return fail(BSM_ERR_ARG, "negative nrhs");
+    if (nrhs == 0) return 0;
+    if (!x_host || !y_host) return fail(BSM_ERR_ARG, "x or y is null");
+    if (h->device == BSM_DEVICE_NONE) return fail(BSM_ERR_CUDA, "host-only handle: no device, and there is no CPU fallback");
+    const int64_t s = dtype_size(h->H.dtype);
+    const int64_t nout = (op == BSM_OP_N) ? h->H.nrows : h->H.ncols;
+    const int64_t nin = (op == BSM_OP_N) ? h->H.ncols : h->H.nrows;
+    if (nrhs > 1 && (ldx < nin || ldy < nout)) return fail(BSM_ERR_ARG, "leading dimension too small");
+    std::lock_guard<std::mutex> lock(h->host_mu);
+    DeviceGuard g(h->device);
+    if (!g.ok) return fail(BSM_ERR_CUDA, "cudaSetDevice failed");
+    if (!h->host_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+    const int64_t xb = nin * nrhs * s, yb = nout * nrhs * s;
+    if (h->hx_bytes < xb) {
+        if (h->hx) cudaFree(h->hx);
+        h->hx = nullptr;
+        h->hx_bytes = 0;
+        CUDA_TRY(cudaMalloc(&h->hx, (size_t)xb));
+        h->hx_bytes = xb;
+    }
+    if (h->hy_bytes < yb) {
+        if (h->hy) cudaFree(h->hy);
+        h->hy = nullptr;
+        h->hy_bytes = 0;
+        CUDA_TRY(cudaMalloc(&h->hy, (size_t)yb));
+        h->hy_bytes = yb;
+    }
+    cudaStream_t st = h->host_stream;
+    CUDA_TRY(cudaMemcpy2DAsync(h->hx, (size_t)(nin * s), x_host, (size_t)((nrhs > 1 ? ldx : nin) * s),
+                               (size_t)(nin * s), (size_t)nrhs, cudaMemcpyHostToDevice, st));
+    if (!beta_is_false)
+        CUDA_TRY(cudaMemcpy2DAsync(h->hy, (size_t)(nout * s), y_host, (size_t)((nrhs > 1 ? ldy : nout) * s),
+                                   (size_t)(nout * s), (size_t)nrhs, cudaMemcpyHostToDevice, st));
+    if (int rc = bsm_mul(h, op, alpha, beta, beta_is_false, h->hx, nin, h->hy, nout, nrhs, (void *)st)) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(y_host, (size_t)((nrhs > 1 ? ldy : nout) * s), h->hy, (size_t)(nout * s),
+                               (size_t)(nout * s), (size_t)nrhs, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- queries -------------------------------------------------------------------------------
+int64_t bsm_nnz(bsm_handle h) { return h ? h->H.nnz : BSM_ERR_ARG; }
+int64_t bsm_stored_entries(bsm_handle h) { return h ? h->H.stored : BSM_ERR_ARG; }
+int bsm_size(bsm_handle h, int64_t *nrows, int64_t *ncols) {
+    if (int rc = check_handle(h)) return rc;
+    if (nrows) *nrows = h->H.nrows;
+    if (ncols) *ncols = h->H.ncols;
+    return 0;
+}
+int bsm_dtype_of(bsm_handle h) { return h ? h->H.dtype : BSM_ERR_ARG; }
+int bsm_kind_of(bsm_handle h) { return h ? h->H.kind : BSM_ERR_ARG; }
+
+int bsm_work(bsm_handle h, int op, int64_t nrhs, int beta_used, double *bytes, double *flops,
+             double *index_table_bytes) {
+    if (int rc = check_handle(h)) return rc;
+    if (op < BSM_OP_N || op > BSM_OP_C) return fail(BSM_ERR_ARG, "bad op");
+    const HostMatrix &H = h->H;
+    const HostPlan &P = H.plan[op == BSM_OP_N ? 0 : 1];
+    const double s = dtype_size(H.dtype);
+    const double tab = (double)P.contrib.size() * sizeof(bsm_contrib) + (double)P.slices.size() * sizeof(bsm_slice) +
+                       (double)H.sets.pool.size() * 4 + (double)H.sets.len.size() * 16 +
+                       (double)P.gather_rows.size() * 12 + (double)P.gather_pos.size() * 8;
+    if (bytes)
+        *bytes = (double)H.stored * s + ((double)P.in_dim + (double)P.out_dim * (beta_used ? 2.0 : 1.0)) * s * (double)nrhs + tab;
+    if (flops) *flops = (H.dtype == BSM_C64 ? 8.0 : 2.0) * (double)P.applied_entries * (double)nrhs;
+    if (index_table_bytes) *index_table_bytes = tab;
+    return 0;
+}
+
+int bsm_launch_count(bsm_handle h, int op) {
+    if (!h || op < BSM_OP_N || op > BSM_OP_C) return BSM_ERR_ARG;
+    const HostPlan &P = h->H.plan[op == BSM_OP_N ? 0 : 1];
+    return (P.slices.empty() ? 0 : 1) + (P.gather_rows.empty() ? 0 : 1);
+}
+
+}  // extern "C"
+
+// ---- table export --------------------------------------------------------------------------
+namespace {
+struct TabView {
+    const void *p = nullptr;
+    int64_t count = -1;
+    int64_t elem = 0;
+    bool device_arena = false;
+};
+template <class U>
+TabView view(const std::vector<U> &v) {
+    TabView t;
+    t.p = v.data();
+    t.count = (int64_t)v.size();
+    t.elem = (int64_t)sizeof(U);
+    return t;
+}
+TabView table_view(bsm_handle h, int table, int plan, std::vector<int32_t> &tmp32) {
+    const HostMatrix &H = h->H;
+    TabView t;
+    if (plan < 0 || plan > 1) return t;
+    const HostPlan &P = H.plan[plan];
+    switch (table) {
+    case BSM_TAB_ARENA:
+        t.count = H.arena_elems;
+        t.elem = dtype_size(H.dtype);
+        t.device_arena = true;
+        return t;
+    case BSM_TAB_BLOCK_OFF: return view(H.block_off);
+    case BSM_TAB_BLOCK_M:
+        tmp32.clear();
+        for (auto &b : H.blocks) tmp32.push_back(b.m);
+        return view(tmp32);
+    case BSM_TAB_BLOCK_N:
+        tmp32.clear();
+        for (auto &b : H.blocks) tmp32.push_back(b.n);
+        return view(tmp32);
+    case BSM_TAB_SET_LEN: return view(H.sets.len);
+    case BSM_TAB_SET_START: return view(H.sets.start);
+    case BSM_TAB_SET_POOL_OFF: return view(H.sets.pool_off);
+    case BSM_TAB_POOL: return view(H.sets.pool);
+    case BSM_TAB_CONTRIB: return view(P.contrib);
+    case BSM_TAB_SLICE: return view(P.slices);
+    case BSM_TAB_GATHER_ROWS: return view(P.gather_rows);
+    case BSM_TAB_GATHER_PTR: return view(P.gather_ptr);
+    case BSM_TAB_GATHER_POS: return view(P.gather_pos);
+    case BSM_TAB_GROUP_PTR: return view(P.group_ptr);
+    case BSM_TAB_GROUP_SET: return view(P.group_set);
+    }
+    return t;
+}
+}  // namespace
+
+extern "C" {
+
+int64_t bsm_table_count(bsm_handle h, int table, int plan) {
+    if (!h) return BSM_ERR_ARG;
+    std::vector<int32_t> tmp;
+    return table_view(h, table, plan, tmp).count;
+}
+
+int bsm_table_copy(bsm_handle h, int table, int plan, void *dst, int64_t dst_bytes) {
+    if (int rc = check_handle(h)) return rc;
+    std::vector<int32_t> tmp;
+    TabView t = table_view(h, table, plan, tmp);
+    if (t.count < 0) return fail(BSM_ERR_ARG, "unknown table");
+    if (dst_bytes < t.count * t.elem) return fail(BSM_ERR_ARG, "destination too small");
+    if (t.count == 0) return 0;
+    if (!dst) return fail(BSM_ERR_ARG, "dst is null");
+    if (t.device_arena) {
+        if (h->device == BSM_DEVICE_NONE) return fail(BSM_ERR_CUDA, "host-only handle has no arena");
+        DeviceGuard g(h->device);
+        CUDA_TRY(cudaMemcpy(dst, h->arena, (size_t)(t.count * t.elem), cudaMemcpyDeviceToHost));
+    } else {
+        std::memcpy(dst, t.p, (size_t)(t.count * t.elem));
+    }
+    return 0;
+}
+
+// ---- device helpers ------------------------------------------------------------------------
+int bsm_device_count(int *count) {
+    if (!count) return fail(BSM_ERR_ARG, "count is null");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(BSM_ERR_CUDA, cudaGetErrorString(e));
+    }
+    return 0;
+}
+int bsm_malloc(int device, size_t bytes, void **dev_ptr) {
+    if (!dev_ptr) return fail(BSM_ERR_ARG, "dev_ptr is null");
+    DeviceGuard g(device);
+    if (!g.ok) return fail(BSM_ERR_CUDA, "cudaSetDevice failed");
+    CUDA_TRY(cudaMalloc(dev_ptr, bytes ? bytes : 16));
+    return 0;
+}
+int bsm_free(int device, void *dev_ptr) {
+    DeviceGuard g(device);
+    if (!g.ok) return fail(BSM_ERR_CUDA, "cudaSetDevice failed");
+    CUDA_TRY(cudaFree(dev_ptr));
+    return 0;
+}
+int bsm_memcpy_h2d(void *dev_dst, const void *host_src, size_t bytes) {
+    CUDA_TRY(cudaMemcpy(dev_dst, host_src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+int bsm_memcpy_d2h(void *host_dst, const void *dev_src, size_t bytes) {
+    CUDA_TRY(cudaMemcpy(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int bsm_synchronize(int device) {
+    DeviceGuard g(device);
+    if (!g.ok) return fail(BSM_ERR_CUDA, "cudaSetDevice failed");
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,302 @@
+// kernels.cuh — sm_100a kernels of the block-sparse multiply.
+//
+//   gather_gemv_kernel<T>  one CTA (128 threads) per work item ("slice"): owner-computes gather
+//                          GEMV over all contributions of an output segment, direct coalesced
+//                          global loads of the column-major blocks (128-bit when the leading
+//                          dimension allows it), x segments staged in shared memory, warp-shuffle
+//                          reductions for the T-form (dot-product) contributions, alpha/beta fused
+//                          into the single write of every owned y row.
+//   gather_finalize_kernel<T>  reduces scratch partial vectors through the per-row gather lists in a
+//                          fixed order (deterministic, no atomics).
+//
+// Replaces the per-colour fork/join + per-block LinearAlgebra.mul! of
+// /root/reference/src/blockmatrix.jl:231-244, src/symmetricblockmatrix.jl:392-432 and
+// src/vbcrs.jl:273-286, 313-326.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/bsm_b200.h"
+
+namespace bsm {
+
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+constexpr int kXsCap = 1024;  // x-segment staging capacity (elements)
+
+struct alignas(16) cplx {
+    double re, im;
+};
+
+// ---- element arithmetic ----------------------------------------------------------------------
+template <class T>
+struct El;
+template <>
+struct El<float> {
+    static __device__ __forceinline__ float zero() { return 0.f; }
+    static __device__ __forceinline__ float conj(float a) { return a; }
+    static __device__ __forceinline__ void fma(float &acc, float a, float b) { acc = fmaf(a, b, acc); }
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float shfl_xor(float a, int m) { return __shfl_xor_sync(0xffffffffu, a, m); }
+};
+template <>
+struct El<double> {
+    static __device__ __forceinline__ double zero() { return 0.0; }
+    static __device__ __forceinline__ double conj(double a) { return a; }
+    static __device__ __forceinline__ void fma(double &acc, double a, double b) { acc = ::fma(a, b, acc); }
+    static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
+    static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+    static __device__ __forceinline__ double shfl_xor(double a, int m) { return __shfl_xor_sync(0xffffffffu, a, m); }
+};
+template <>
+struct El<cplx> {
+    static __device__ __forceinline__ cplx zero() { return cplx{0.0, 0.0}; }
+    static __device__ __forceinline__ cplx conj(cplx a) { return cplx{a.re, -a.im}; }
+    static __device__ __forceinline__ void fma(cplx &acc, cplx a, cplx b) {
+        acc.re = ::fma(a.re, b.re, acc.re);
+        acc.re = ::fma(-a.im, b.im, acc.re);
+        acc.im = ::fma(a.re, b.im, acc.im);
+        acc.im = ::fma(a.im, b.re, acc.im);
+    }
+    static __device__ __forceinline__ cplx mul(cplx a, cplx b) {
+        return cplx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+    }
+    static __device__ __forceinline__ cplx add(cplx a, cplx b) { return cplx{a.re + b.re, a.im + b.im}; }
+    static __device__ __forceinline__ cplx shfl_xor(cplx a, int m) {
+        return cplx{__shfl_xor_sync(0xffffffffu, a.re, m), __shfl_xor_sync(0xffffffffu, a.im, m)};
+    }
+};
+
+// ---- streaming (evict-first) loads of V consecutive elements ---------------------------------
+template <class T, int V>
+struct Pack {
+    T v[V];
+};
+
+template <class T, int V>
+__device__ __forceinline__ Pack<T, V> load_stream(const T *p) {
+    Pack<T, V> r;
+    constexpr int bytes = (int)sizeof(T) * V;
+    if constexpr (bytes == 16) {
+        const int4 q = __ldcs(reinterpret_cast<const int4 *>(p));
+        *reinterpret_cast<int4 *>(&r) = q;
+    } else if constexpr (bytes == 8) {
+        const int2 q = __ldcs(reinterpret_cast<const int2 *>(p));
+        *reinterpret_cast<int2 *>(&r) = q;
+    } else {
+        static_assert(bytes == 4, "unsupported pack");
+        const int q = __ldcs(reinterpret_cast<const int *>(p));
+        *reinterpret_cast<int *>(&r) = q;
+    }
+    return r;
+}
+
+// ---- kernel arguments ------------------------------------------------------------------------
+template <class T>
+struct MulArgs {
+    const T *arena;
+    const bsm_contrib *contrib;
+    const bsm_slice *slices;
+    const int32_t *set_len;
+    const int32_t *set_start;
+    const int64_t *set_pool_off;
+    const int32_t *pool;
+    const T *x;
+    T *y;
+    T *scratch;
+    T alpha, beta;
+    int32_t nslices;
+    int32_t beta_false;
+    int32_t conj;
+};
+
+struct SetRef {
+    int32_t start;
+    const int32_t *pool;
+    __device__ __forceinline__ int32_t at(int32_t k) const { return start >= 0 ? start + k : __ldg(pool + k); }
+};
+
+template <class T>
+__device__ __forceinline__ SetRef set_ref(const MulArgs<T> &a, int32_t s) {
+    SetRef r;
+    r.start = __ldg(a.set_start + s);
+    r.pool = a.pool + __ldg(a.set_pool_off + s);
+    return r;
+}
+
+// ---- N-form: outputs along the rows of the block ---------------------------------------------
+// thread -> (row vector iv, column phase c); columns j = c, c+P, ...; acc[V] lives in registers
+template <class T, int V, bool CONJ>
+__device__ __forceinline__ void nform_chunk(const T *__restrict__ base, int32_t m, int32_t cn, int32_t c,
+                                            int32_t P, const T *__restrict__ xs, T (&acc)[V]) {
+    int32_t j = c;
+    for (; j + 3 * P < cn; j += 4 * P) {
+        Pack<T, V> v0 = load_stream<T, V>(base + (int64_t)j * m);
+        Pack<T, V> v1 = load_stream<T, V>(base + (int64_t)(j + P) * m);
+        Pack<T, V> v2 = load_stream<T, V>(base + (int64_t)(j + 2 * P) * m);
+        Pack<T, V> v3 = load_stream<T, V>(base + (int64_t)(j + 3 * P) * m);
+        const T x0 = xs[j], x1 = xs[j + P], x2 = xs[j + 2 * P], x3 = xs[j + 3 * P];
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            El<T>::fma(acc[q], CONJ ? El<T>::conj(v0.v[q]) : v0.v[q], x0);
+            El<T>::fma(acc[q], CONJ ? El<T>::conj(v1.v[q]) : v1.v[q], x1);
+            El<T>::fma(acc[q], CONJ ? El<T>::conj(v2.v[q]) : v2.v[q], x2);
+            El<T>::fma(acc[q], CONJ ? El<T>::conj(v3.v[q]) : v3.v[q], x3);
+        }
+    }
+    for (; j < cn; j += P) {
+        Pack<T, V> v0 = load_stream<T, V>(base + (int64_t)j * m);
+        const T x0 = xs[j];
+#pragma unroll
+        for (int q = 0; q < V; ++q) El<T>::fma(acc[q], CONJ ? El<T>::conj(v0.v[q]) : v0.v[q], x0);
+    }
+}
+
+// ---- T-form: outputs along the columns of the block ------------------------------------------
+// one warp per column, lanes stride over the rows, shuffle reduction
+template <class T, int V, bool CONJ>
+__device__ __forceinline__ T tform_column(const T *__restrict__ col, int32_t cm, int lane,
+                                          const T *__restrict__ xs) {
+    T s0 = El<T>::zero(), s1 = El<T>::zero();
+    int32_t i = lane * V;
+    for (; i + 32 * V < cm; i += 64 * V) {
+        Pack<T, V> v0 = load_stream<T, V>(col + i);
+        Pack<T, V> v1 = load_stream<T, V>(col + i + 32 * V);
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            El<T>::fma(s0, CONJ ? El<T>::conj(v0.v[q]) : v0.v[q], xs[i + q]);
+            El<T>::fma(s1, CONJ ? El<T>::conj(v1.v[q]) : v1.v[q], xs[i + 32 * V + q]);
+        }
+    }
+    if (i < cm) {
+        Pack<T, V> v0 = load_stream<T, V>(col + i);
+#pragma unroll
+        for (int q = 0; q < V; ++q) El<T>::fma(s0, CONJ ? El<T>::conj(v0.v[q]) : v0.v[q], xs[i + q]);
+    }
+    T s = El<T>::add(s0, s1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = El<T>::add(s, El<T>::shfl_xor(s, o));
+    return s;
+}
+
+template <class T, int V, bool CONJ>
+__device__ __forceinline__ void slice_body(const MulArgs<T> &a, const bsm_slice &sl, T *xs, T *red,
+                                           T *accT) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int32_t r0 = sl.r0, h = sl.r1 - sl.r0;
+    const int32_t hv = (h + V - 1) / V;          // row vectors (h % V == 0 whenever V > 1)
+    const int32_t P = kThreads / hv;             // column phases, >= 1
+    const bool active = t < P * hv;
+    const int32_t iv = t % hv, c = t / hv;
+    T acc[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) acc[q] = El<T>::zero();
+    accT[t] = El<T>::zero();
+
+    for (int32_t ci = sl.c_begin; ci < sl.c_end; ++ci) {
+        const bsm_contrib cb = a.contrib[ci];
+        const SetRef in = set_ref(a, cb.in_set);
+        const T *blk = a.arena + cb.off;
+        if (cb.form == 0) {
+            // rows [r0, r0+h) ∩ [0, out_len) of every column
+            const bool rows_ok = active && (r0 + iv * V) < cb.out_len;
+            for (int32_t j0 = 0; j0 < cb.n; j0 += kXsCap) {
+                const int32_t cn = min(kXsCap, cb.n - j0);
+                __syncthreads();
+                for (int32_t k = t; k < cn; k += kThreads) xs[k] = a.x[in.at(j0 + k)];
+                __syncthreads();
+                if (rows_ok)
+                    nform_chunk<T, V, CONJ>(blk + (int64_t)j0 * cb.m + r0 + iv * V, cb.m, cn, c, P, xs, acc);
+            }
+        } else {
+            // columns [r0, r0+h) ∩ [0, out_len), dot products over all rows
+            const int32_t hc = min(h, cb.out_len - r0);
+            for (int32_t i0 = 0; i0 < cb.m; i0 += kXsCap) {
+                const int32_t cm = min(kXsCap, cb.m - i0);
+                __syncthreads();
+                for (int32_t k = t; k < cm; k += kThreads) xs[k] = a.x[in.at(i0 + k)];
+                __syncthreads();
+                for (int32_t jj = warp; jj < hc; jj += kWarps) {
+                    const T s = tform_column<T, V, CONJ>(blk + (int64_t)(r0 + jj) * cb.m + i0, cm, lane, xs);
+                    if (lane == 0) accT[jj] = El<T>::add(accT[jj], s);
+                }
+            }
+        }
+    }
+    // reduce the column phases, add the T-form part, write
+    __syncthreads();
+    if (active) {
+#pragma unroll
+        for (int q = 0; q < V; ++q) red[c * h + iv * V + q] = acc[q];
+    }
+    __syncthreads();
+    if (t < h) {
+        T tot = accT[t];
+        for (int32_t p = 0; p < P; ++p) tot = El<T>::add(tot, red[p * h + t]);
+        if (sl.flags & 1) {
+            const SetRef out = set_ref(a, sl.out_set);
+            const int32_t row = out.at(r0 + t);
+            T v = El<T>::mul(a.alpha, tot);
+            if (!a.beta_false) v = El<T>::add(v, El<T>::mul(a.beta, a.y[row]));
+            a.y[row] = v;
+        } else {
+            a.scratch[sl.scratch_off + t] = tot;
+        }
+    }
+}
+
+template <class T, int VMAX>
+__global__ void __launch_bounds__(kThreads) gather_gemv_kernel(const MulArgs<T> a) {
+    __shared__ __align__(16) unsigned char xs_raw[kXsCap * sizeof(T)];
+    __shared__ __align__(16) unsigned char red_raw[kThreads * VMAX * sizeof(T)];
+    __shared__ __align__(16) unsigned char acc_raw[kThreads * sizeof(T)];
+    T *xs = reinterpret_cast<T *>(xs_raw);
+    T *red = reinterpret_cast<T *>(red_raw);
+    T *accT = reinterpret_cast<T *>(acc_raw);
+    const bsm_slice sl = a.slices[blockIdx.x];
+    const bool vec = (VMAX > 1) && (sl.flags & 2);
+    if (a.conj) {
+        if (vec)
+            slice_body<T, VMAX, true>(a, sl, xs, red, accT);
+        else
+            slice_body<T, 1, true>(a, sl, xs, red, accT);
+    } else {
+        if (vec)
+            slice_body<T, VMAX, false>(a, sl, xs, red, accT);
+        else
+            slice_body<T, 1, false>(a, sl, xs, red, accT);
+    }
+}
+
+template <class T>
+struct FinalizeArgs {
+    const int32_t *rows;
+    const int64_t *ptr;
+    const int64_t *pos;
+    const T *scratch;
+    T *y;
+    T alpha, beta;
+    int64_t n;
+    int32_t beta_false;
+};
+
+template <class T>
+__global__ void __launch_bounds__(256) gather_finalize_kernel(const FinalizeArgs<T> a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int32_t rr = a.rows[i];
+    const int32_t row = rr & 0x7fffffff;
+    T s = El<T>::zero();
+    for (int64_t k = a.ptr[i]; k < a.ptr[i + 1]; ++k) s = El<T>::add(s, a.scratch[a.pos[k]]);
+    T v = El<T>::mul(a.alpha, s);
+    if (rr < 0) {
+        v = El<T>::add(v, a.y[row]);  // a direct slice already wrote alpha*acc + beta*y here
+    } else if (!a.beta_false) {
+        v = El<T>::add(v, El<T>::mul(a.beta, a.y[row]));
+    }
+    a.y[row] = v;
+}
+
+}  // namespace bsm

@@ -1,0 +1,247 @@
+// pack.cpp — host packer: index-set deduplication, arena layout, plan construction.
+// Everything here is deterministic (no hashing order leaks into the tables) so the Python mirror
+// (blocksparsematrices.jl_b200/packing.py) reproduces every table bit for bit.
+#include "plan.h"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+namespace bsm {
+
+// ---------------------------------------------------------------------------- index sets
+static uint64_t fnv1a(const int32_t *p, int64_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (int64_t i = 0; i < n; ++i) {
+        h ^= (uint32_t)p[i];
+        h *= 1099511628211ull;
+    }
+    return h ^ (uint64_t)n;
+}
+
+int32_t IndexSets::add_range(int64_t start0, int64_t n) {
+    // key space of ranges: hash of (start, len) with a tag so it cannot collide silently —
+    // equality is always re-checked.
+    uint64_t key = ((uint64_t)start0 * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)n << 1) ^ 1ull;
+    auto &cands = by_hash[key];
+    for (int32_t id : cands)
+        if (start[id] == (int32_t)start0 && len[id] == (int32_t)n) return id;
+    int32_t id = (int32_t)len.size();
+    len.push_back((int32_t)n);
+    start.push_back((int32_t)start0);
+    pool_off.push_back(0);
+    cands.push_back(id);
+    return id;
+}
+
+int32_t IndexSets::add_vector(const int64_t *idx1, int64_t n, int64_t limit) {
+    bool contiguous = n > 0;
+    for (int64_t k = 0; k < n; ++k) {
+        if (idx1[k] < 1 || idx1[k] > limit) return -1;
+        if (idx1[k] != idx1[0] + k) contiguous = false;
+    }
+    if (contiguous) return add_range(idx1[0] - 1, n);
+    std::vector<int32_t> tmp((size_t)n);
+    for (int64_t k = 0; k < n; ++k) tmp[(size_t)k] = (int32_t)(idx1[k] - 1);
+    uint64_t key = fnv1a(tmp.data(), n) << 1;  // even keys: vectors, odd keys: ranges
+    auto &cands = by_hash[key];
+    for (int32_t id : cands) {
+        if (start[id] < 0 && len[id] == (int32_t)n &&
+            (n == 0 || std::memcmp(pool.data() + pool_off[id], tmp.data(), (size_t)n * 4) == 0))
+            return id;
+    }
+    int32_t id = (int32_t)len.size();
+    len.push_back((int32_t)n);
+    start.push_back(-1);
+    pool_off.push_back((int64_t)pool.size());
+    pool.insert(pool.end(), tmp.begin(), tmp.end());
+    cands.push_back(id);
+    return id;
+}
+
+// ---------------------------------------------------------------------------- arena
+void layout_arena(HostMatrix &M) {
+    const int64_t s = dtype_size(M.dtype);
+    const int64_t align = kArenaAlignBytes / s;
+    M.block_off.resize(M.blocks.size());
+    int64_t off = 0, stored = 0;
+    for (size_t b = 0; b < M.blocks.size(); ++b) {
+        M.block_off[b] = off;
+        const int64_t e = (int64_t)M.blocks[b].m * M.blocks[b].n;
+        stored += e;
+        off += (e + align - 1) / align * align;
+    }
+    M.stored = stored;
+    M.arena_elems = off + align;  // tail slack: vector loads may over-read up to 15 bytes
+}
+
+// ---------------------------------------------------------------------------- plan
+std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, int64_t out_dim,
+                       int64_t in_dim, const PlanParams &pp, HostPlan &P) {
+    const IndexSets &S = M.sets;
+    const int64_t s = dtype_size(M.dtype);
+    const int V = dtype_vec(M.dtype);
+    const int64_t own_lo = pp.own_hi < 0 ? 0 : pp.own_lo;
+    const int64_t own_hi = pp.own_hi < 0 ? out_dim : pp.own_hi;
+    P = HostPlan();
+    P.out_dim = out_dim;
+    P.in_dim = in_dim;
+
+    // 1. groups in order of first appearance of their output set; drop groups with no owned output
+    std::vector<int32_t> group_of_set(S.len.size(), -1);
+    std::vector<int32_t> gset;
+    std::vector<std::vector<int32_t>> members;
+    for (size_t c = 0; c < ir.size(); ++c) {
+        const int32_t os = ir[c].out_set;
+        if (os < 0 || (size_t)os >= S.len.size()) return "bad output set";
+        if (group_of_set[os] == -1) {
+            bool any = false;
+            for (int64_t k = 0; k < S.len[os] && !any; ++k) {
+                const int64_t r = S.at(os, k);
+                any = (r >= own_lo && r < own_hi);
+            }
+            if (!any) {
+                group_of_set[os] = -2;  // dropped
+            } else {
+                group_of_set[os] = (int32_t)gset.size();
+                gset.push_back(os);
+                members.emplace_back();
+            }
+        }
+        if (group_of_set[os] >= 0) members[group_of_set[os]].push_back((int32_t)c);
+    }
+    const size_t G = gset.size();
+
+    // 2. contributions grouped (stable), CSR pointer = block-row pointer / transposed index
+    P.group_ptr.assign(G + 1, 0);
+    P.group_set.assign(gset.begin(), gset.end());
+    for (size_t g = 0; g < G; ++g) {
+        P.group_ptr[g + 1] = P.group_ptr[g] + (int64_t)members[g].size();
+        for (int32_t c : members[g]) {
+            const ContribIR &ci = ir[c];
+            const BlockSrc &b = M.blocks[ci.block];
+            bsm_contrib d;
+            d.off = M.block_off[ci.block];
+            d.m = b.m;
+            d.n = b.n;
+            d.in_set = ci.in_set;
+            d.form = ci.form;
+            d.out_len = ci.out_len;
+            d.block = ci.block;
+            if (ci.out_len > S.len[gset[g]]) return "contribution longer than its output segment";
+            if (S.len[ci.in_set] < (ci.form == 0 ? b.n : b.m)) return "input set shorter than block";
+            P.contrib.push_back(d);
+            P.applied_entries += (int64_t)b.m * b.n;
+        }
+    }
+
+    // 3. ownership: first come claims; a group is direct iff none of its rows is claimed, it has no
+    //    repeated row, and it lies entirely inside the owned range
+    std::vector<uint8_t> claimed((size_t)out_dim, 0);
+    std::vector<int32_t> stamp((size_t)out_dim, -1);
+    P.group_direct.assign(G, 0);
+    for (size_t g = 0; g < G; ++g) {
+        const int32_t os = gset[g];
+        bool direct = true;
+        for (int64_t k = 0; k < S.len[os]; ++k) {
+            const int64_t r = S.at(os, k);
+            if (r < own_lo || r >= own_hi || claimed[(size_t)r] || stamp[(size_t)r] == (int32_t)g) {
+                direct = false;
+                break;
+            }
+            stamp[(size_t)r] = (int32_t)g;
+        }
+        if (direct)
+            for (int64_t k = 0; k < S.len[os]; ++k) claimed[(size_t)S.at(os, k)] = 1;
+        P.group_direct[g] = direct;
+    }
+
+    // 4. slices: cut every output segment into pieces of <= kMaxSliceHeight outputs, more pieces if
+    //    the segment is heavy (work_target_bytes), never thinner than 128 bytes of a column
+    struct Tmp {
+        bsm_slice s;
+        int64_t work;
+        int64_t order;
+    };
+    std::vector<Tmp> tmp;
+    const int64_t hmin = std::max<int64_t>(1, 128 / s);
+    for (size_t g = 0; g < G; ++g) {
+        const int64_t L = S.len[gset[g]];
+        if (L == 0) continue;
+        int64_t W = 0;
+        bool vec_ok = true;
+        for (int64_t c = P.group_ptr[g]; c < P.group_ptr[g + 1]; ++c) {
+            W += (int64_t)P.contrib[c].m * P.contrib[c].n * s;
+            if (P.contrib[c].m % V != 0) vec_ok = false;
+        }
+        if (L % V != 0) vec_ok = false;
+        int64_t pieces = (L + kMaxSliceHeight - 1) / kMaxSliceHeight;
+        const int64_t by_work = (W + pp.work_target_bytes - 1) / pp.work_target_bytes;
+        const int64_t max_pieces = std::max<int64_t>(1, L / hmin);
+        pieces = std::max(pieces, std::min(by_work, max_pieces));
+        int64_t ps = (L + pieces - 1) / pieces;
+        ps = (ps + V - 1) / V * V;
+        ps = std::min<int64_t>(ps, kMaxSliceHeight);
+        for (int64_t r0 = 0; r0 < L; r0 += ps) {
+            Tmp t;
+            t.s.out_set = gset[g];
+            t.s.r0 = (int32_t)r0;
+            t.s.r1 = (int32_t)std::min(L, r0 + ps);
+            t.s.c_begin = (int32_t)P.group_ptr[g];
+            t.s.c_end = (int32_t)P.group_ptr[g + 1];
+            t.s.flags = (P.group_direct[g] ? kSliceDirect : 0) | (vec_ok ? kSliceVecOk : 0);
+            t.s.scratch_off = 0;
+            t.work = W * (t.s.r1 - t.s.r0) / L;
+            t.order = (int64_t)tmp.size();
+            tmp.push_back(t);
+        }
+    }
+    // scratch offsets are assigned in creation order (before the scheduling sort)
+    int64_t scratch = 0;
+    for (auto &t : tmp) {
+        if (!(t.s.flags & kSliceDirect)) {
+            t.s.scratch_off = scratch;
+            scratch += t.s.r1 - t.s.r0;
+        }
+    }
+    P.scratch_elems = scratch;
+
+    // 5. gather lists: every owned row that is not claimed by a direct group, or that receives
+    //    partial sums; partials are listed in slice creation order (fixed reduction order)
+    std::vector<int64_t> cnt((size_t)out_dim + 1, 0);
+    for (const auto &t : tmp) {
+        if (t.s.flags & kSliceDirect) continue;
+        for (int64_t k = t.s.r0; k < t.s.r1; ++k) {
+            const int64_t r = S.at(t.s.out_set, k);
+            if (r >= own_lo && r < own_hi) cnt[(size_t)r + 1]++;
+        }
+    }
+    std::vector<int64_t> rowslot((size_t)out_dim, -1);
+    P.gather_ptr.push_back(0);
+    for (int64_t r = own_lo; r < own_hi; ++r) {
+        if (cnt[(size_t)r + 1] > 0 || !claimed[(size_t)r]) {
+            rowslot[(size_t)r] = (int64_t)P.gather_rows.size();
+            P.gather_rows.push_back((int32_t)r | (claimed[(size_t)r] ? (int32_t)0x80000000 : 0));
+            P.gather_ptr.push_back(P.gather_ptr.back() + cnt[(size_t)r + 1]);
+        }
+    }
+    P.gather_pos.assign((size_t)P.gather_ptr.back(), 0);
+    std::vector<int64_t> fill(P.gather_ptr.begin(), P.gather_ptr.end() - 1);
+    for (const auto &t : tmp) {
+        if (t.s.flags & kSliceDirect) continue;
+        for (int64_t k = t.s.r0; k < t.s.r1; ++k) {
+            const int64_t r = S.at(t.s.out_set, k);
+            if (r >= own_lo && r < own_hi)
+                P.gather_pos[(size_t)fill[(size_t)rowslot[(size_t)r]]++] = t.s.scratch_off + (k - t.s.r0);
+        }
+    }
+
+    // 6. schedule: heaviest slices first (stable)
+    std::stable_sort(tmp.begin(), tmp.end(),
+                     [](const Tmp &a, const Tmp &b) { return a.work > b.work; });
+    P.slices.reserve(tmp.size());
+    for (const auto &t : tmp) P.slices.push_back(t.s);
+    return std::string();
+}
+
+}  // namespace bsm

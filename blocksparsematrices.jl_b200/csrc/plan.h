@@ -1,0 +1,111 @@
+// plan.h — host-side intermediate representation and device plan of libbsm_b200.
+//
+// The three reference storage types (/root/reference/src/blockmatrix.jl:26-34,
+// src/symmetricblockmatrix.jl:33-44, src/vbcrs.jl:36-43) are lowered to ONE device layout:
+//
+//   arena      every dense block, column-major as Julia stores it, verbatim, each block starting at
+//              a 128-byte aligned offset of a single HBM allocation
+//   sets       deduplicated index vectors ("index sets"): a contiguous range is (start, len), an
+//              arbitrary vector is a slice of one Int32 pool (0-based)
+//   plan[2]    plan 0 serves op N, plan 1 serves op T and op C (conj applied on the fly).
+//              A plan is a list of *contributions*  y[out] += op(B) x[in]  (N-form: outputs along the
+//              block's rows; T-form: outputs along its columns), grouped by output segment (= the
+//              block-row pointer for plan 0, the transposed index for plan 1), cut into work items
+//              ("slices"). A slice either owns its output rows (writes y directly, alpha/beta fused)
+//              or writes a partial vector to scratch that a gather pass reduces in a fixed order —
+//              no atomics anywhere, results are run-to-run deterministic.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/bsm_b200.h"
+
+namespace bsm {
+
+static_assert(sizeof(bsm_contrib) == 32, "bsm_contrib must be 32 bytes");
+static_assert(sizeof(bsm_slice) == 32, "bsm_slice must be 32 bytes");
+
+constexpr int kSliceDirect = 1;
+constexpr int kSliceVecOk = 2;
+constexpr int kMaxSliceHeight = 128;   // outputs per work item (one CTA of 128 threads)
+constexpr int64_t kArenaAlignBytes = 128;
+
+inline int dtype_size(int dtype) { return dtype == BSM_F32 ? 4 : dtype == BSM_F64 ? 8 : 16; }
+// elements per 16-byte vector load
+inline int dtype_vec(int dtype) { return 16 / dtype_size(dtype); }
+
+// ---- index sets ------------------------------------------------------------------------------
+struct IndexSets {
+    std::vector<int32_t> len, start;
+    std::vector<int64_t> pool_off;
+    std::vector<int32_t> pool;
+    std::unordered_map<uint64_t, std::vector<int32_t>> by_hash;
+
+    // 1-based Int64 vector as Julia holds it; every value must be in [1, limit]. Returns the set id
+    // (existing id if an identical vector was added before) or -1 on a bad index.
+    int32_t add_vector(const int64_t *idx1, int64_t n, int64_t limit);
+    // 0-based contiguous range
+    int32_t add_range(int64_t start0, int64_t n);
+    inline int64_t at(int32_t s, int64_t k) const {
+        return start[s] >= 0 ? (int64_t)start[s] + k : (int64_t)pool[pool_off[s] + k];
+    }
+};
+
+// ---- blocks ----------------------------------------------------------------------------------
+struct BlockSrc {
+    const void *host;   // host pointer (read during create only)
+    int32_t m, n;       // logical size of the block as it will sit in the arena
+    bool transposed;    // host holds the n x m parent of a lazy transpose wrapper
+};
+
+// ---- plan ------------------------------------------------------------------------------------
+struct ContribIR {
+    int32_t block;
+    int32_t form;      // 0 N-form, 1 T-form
+    int32_t out_set;   // output segment (group key)
+    int32_t in_set;
+    int32_t out_len;
+};
+
+struct HostPlan {
+    std::vector<bsm_contrib> contrib;   // grouped by output segment
+    std::vector<int64_t> group_ptr;     // CSR over contrib
+    std::vector<int32_t> group_set;
+    std::vector<uint8_t> group_direct;
+    std::vector<bsm_slice> slices;      // sorted by decreasing work
+    std::vector<int32_t> gather_rows;
+    std::vector<int64_t> gather_ptr;
+    std::vector<int64_t> gather_pos;
+    int64_t scratch_elems = 0;
+    int64_t out_dim = 0, in_dim = 0;
+    int64_t applied_entries = 0;        // Σ m*n over contributions
+};
+
+struct HostMatrix {
+    int dtype = BSM_F64;
+    int kind = BSM_KIND_BLOCKSPARSE;
+    int64_t nrows = 0, ncols = 0;
+    int64_t nnz = 0;             // SparseArrays.nnz semantics
+    int64_t stored = 0;          // entries in the arena
+    std::vector<BlockSrc> blocks;
+    std::vector<int64_t> block_off;    // element offsets, 128-byte aligned
+    int64_t arena_elems = 0;           // including tail slack
+    IndexSets sets;
+    HostPlan plan[2];
+};
+
+struct PlanParams {
+    int64_t own_lo = 0, own_hi = -1;   // owned output range, hi < 0: everything
+    int64_t work_target_bytes = 512 << 10;
+};
+
+// Lays the blocks out in the arena (fills block_off, arena_elems, stored).
+void layout_arena(HostMatrix &M);
+// Groups contributions, decides direct vs scratch ownership, cuts slices, builds the gather lists.
+// Returns an empty string on success, else an error message.
+std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, int64_t out_dim,
+                       int64_t in_dim, const PlanParams &pp, HostPlan &P);
+
+}  // namespace bsm

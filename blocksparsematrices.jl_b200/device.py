@@ -1,0 +1,300 @@
+"""Device-resident operators: the Python counterpart of the Julia package extension.
+
+DeviceMatrix(A) packs a host BlockSparseMatrix / SymmetricBlockMatrix / VBCRS into the HBM arena
+through the C ABI (bsm_create_*) and exposes the multiply (bsm_mul / bsm_mul_host). x and y may be
+NumPy arrays (host: copies happen inside bsm_mul_host) or torch CUDA tensors (device pointers, launched
+on torch's current stream). There is no CPU fallback: without libbsm_b200.so or without a GPU every
+product raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, byref, c_double, c_int64, c_uint8, c_void_p
+
+import numpy as np
+
+from . import _lib as L
+from .host import (AbstractBlockMatrix, BlockSparseMatrix, SymmetricBlockMatrix,
+                   VariableBlockCompressedRowStorage, _Wrapped)
+
+_DT = {np.dtype(np.float32): L.F32, np.dtype(np.float64): L.F64, np.dtype(np.complex128): L.C64}
+_NP = {L.F32: np.dtype(np.float32), L.F64: np.dtype(np.float64), L.C64: np.dtype(np.complex128)}
+_OPS = {"N": L.OP_N, "T": L.OP_T, "C": L.OP_C}
+
+
+def _i64p(a):
+    return a.ctypes.data_as(POINTER(c_int64))
+
+
+def _pool(vecs):
+    ptr = np.zeros(len(vecs) + 1, np.int64)
+    if len(vecs):
+        np.cumsum([len(v) for v in vecs], out=ptr[1:])
+        pool = np.concatenate(vecs) if ptr[-1] > 0 else np.zeros(0, np.int64)
+    else:
+        pool = np.zeros(0, np.int64)
+    return np.ascontiguousarray(pool, dtype=np.int64), ptr
+
+
+def _colmajor(blocks, dt, allow_transposed=False):
+    """Column-major views of the blocks (copies only where the memory is not already column-major of
+    the right dtype). Returns (keepalive list, pointer array, m, n, transposed flags)."""
+    keep, ptrs = [], np.zeros(max(len(blocks), 1), np.uintp)
+    m = np.zeros(len(blocks), np.int64)
+    n = np.zeros(len(blocks), np.int64)
+    tr = np.zeros(len(blocks), np.uint8)
+    for i, b in enumerate(blocks):
+        b = np.asarray(b)
+        if b.ndim != 2:
+            raise ValueError(f"block {i} is not a matrix")
+        m[i], n[i] = b.shape
+        if b.dtype == dt and b.flags.f_contiguous:
+            a = b
+        elif allow_transposed and b.dtype == dt and b.flags.c_contiguous:
+            a = b              # lazy transpose wrapper: memory holds the n x m column-major parent
+            tr[i] = 1
+        else:
+            a = np.asfortranarray(b, dtype=dt)
+        keep.append(a)
+        ptrs[i] = a.__array_interface__["data"][0]
+    return keep, ptrs, m, n, tr
+
+
+class DeviceMatrix:
+    """Opaque handle + size: what `B200(A)` of the Julia extension returns."""
+
+    def __init__(self, A: AbstractBlockMatrix, device: int = -1, variant: int = L.VARIANT_AUTO,
+                 own_rows=None, own_cols=None):
+        lib = L.lib()
+        self.host = A
+        self.size = A.size
+        self.dtype = np.dtype(A.dtype)
+        if self.dtype not in _DT:
+            raise TypeError(f"unsupported element type {self.dtype}; supported: float32, float64, complex128")
+        dt = _DT[self.dtype]
+        opt = L.Options()
+        lib.bsm_default_options(byref(opt))
+        opt.device = device
+        opt.variant = variant
+        if own_rows is not None:
+            opt.own_row_lo, opt.own_row_hi = int(own_rows[0]), int(own_rows[1])
+        if own_cols is not None:
+            opt.own_col_lo, opt.own_col_hi = int(own_cols[0]), int(own_cols[1])
+        h = c_void_p()
+        vp = lambda a: a.ctypes.data_as(POINTER(c_void_p))
+        if isinstance(A, BlockSparseMatrix):
+            keep, ptrs, m, n, _ = _colmajor(A.blocks, self.dtype)
+            rp, rptr = _pool(A.rowindices)
+            cp, cptr = _pool(A.colindices)
+            L.check(lib.bsm_create_blocksparse(dt, A.size[0], A.size[1], len(A.blocks), vp(ptrs), _i64p(m),
+                                               _i64p(n), _i64p(rp), _i64p(rptr), _i64p(cp), _i64p(cptr),
+                                               byref(opt), byref(h)))
+        elif isinstance(A, SymmetricBlockMatrix):
+            keepd, dptrs, dm, dn, _ = _colmajor(A.diagonals, self.dtype)
+            if np.any(dm != dn):
+                raise ValueError("diagonal blocks must be square")
+            keepo, optrs, om, on, _ = _colmajor(A.offdiagonals, self.dtype)
+            dp, dptr = _pool(A.diagonalindices)
+            rp, rptr = _pool(A.rowindices)
+            cp, cptr = _pool(A.colindices)
+            L.check(lib.bsm_create_symmetric(dt, A.size[0], A.size[1], len(A.diagonals), vp(dptrs), _i64p(dm),
+                                             _i64p(dp), _i64p(dptr), len(A.offdiagonals), vp(optrs),
+                                             _i64p(om), _i64p(on), _i64p(rp), _i64p(rptr), _i64p(cp),
+                                             _i64p(cptr), byref(opt), byref(h)))
+        elif isinstance(A, VariableBlockCompressedRowStorage):
+            keep, ptrs, m, n, tr = _colmajor(A.blocks, self.dtype, allow_transposed=True)
+            rowptr = np.ascontiguousarray(A.rowptr, np.int64)
+            cs = np.ascontiguousarray(A.colindices, np.int64)
+            rs = np.ascontiguousarray(A.rowindices, np.int64)
+            L.check(lib.bsm_create_vbcrs(dt, A.size[0], A.size[1], len(rowptr) - 1, len(A.blocks), _i64p(rowptr),
+                                         _i64p(cs), _i64p(rs), vp(ptrs), _i64p(m), _i64p(n),
+                                         tr.ctypes.data_as(POINTER(c_uint8)), byref(opt), byref(h)))
+        else:
+            raise TypeError(f"cannot build a device matrix from {type(A).__name__}")
+        self._h = h
+        self.device = device
+
+    # ---- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            L.lib().bsm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- LinearMap surface
+    @property
+    def shape(self):
+        return self.size
+
+    def adjoint(self):
+        return DeviceAdjoint(self)
+
+    def transpose(self):
+        return DeviceTranspose(self)
+
+    H = property(adjoint)
+    T = property(transpose)
+
+    def __mul__(self, x):
+        return apply(self, "N", x)
+
+    __matmul__ = __mul__
+
+    # ---- queries
+
+    def nnz(self) -> int:
+        return int(L.lib().bsm_nnz(self._h))
+
+    def stored_entries(self) -> int:
+        return int(L.lib().bsm_stored_entries(self._h))
+
+    def work(self, op="N", nrhs=1, beta_used=False):
+        b, f, t = c_double(), c_double(), c_double()
+        L.check(L.lib().bsm_work(self._h, _OPS[op], nrhs, int(beta_used), byref(b), byref(f), byref(t)))
+        return {"bytes": b.value, "flops": f.value, "index_table_bytes": t.value}
+
+    def launch_count(self, op="N") -> int:
+        return int(L.lib().bsm_launch_count(self._h, _OPS[op]))
+
+    def set_variant(self, variant: int):
+        L.check(L.lib().bsm_set_variant(self._h, variant))
+
+    def table(self, table: int, plan: int = 0) -> np.ndarray:
+        """Export one packing table (bit-exact checks)."""
+        lib = L.lib()
+        cnt = lib.bsm_table_count(self._h, table, plan)
+        if cnt < 0:
+            raise L.BsmError(cnt, "unknown table")
+        if table == L.TAB_ARENA:
+            dt = self.dtype
+        elif table in (L.TAB_BLOCK_OFF, L.TAB_SET_POOL_OFF, L.TAB_GATHER_PTR, L.TAB_GATHER_POS, L.TAB_GROUP_PTR):
+            dt = np.dtype(np.int64)
+        elif table == L.TAB_CONTRIB:
+            dt = CONTRIB_DTYPE
+        elif table == L.TAB_SLICE:
+            dt = SLICE_DTYPE
+        else:
+            dt = np.dtype(np.int32)
+        out = np.zeros(cnt, dt)
+        L.check(lib.bsm_table_copy(self._h, table, plan, out.ctypes.data_as(c_void_p), out.nbytes))
+        return out
+
+    # ---- multiply
+    def mul(self, op, x, y=None, alpha=True, beta=False, stream=None):
+        """y = alpha*op(A)*x + beta*y. beta is False (the bool) = Julia's strong zero."""
+        lib = L.lib()
+        nout = self.size[0] if op == "N" else self.size[1]
+        nin = self.size[1] if op == "N" else self.size[0]
+        beta_false = isinstance(beta, (bool, np.bool_)) and not beta
+        a = np.array([alpha], dtype=self.dtype)
+        b = np.array([0 if beta_false else beta], dtype=self.dtype)
+        if _is_torch(x):
+            import torch
+            tdt = _torch_dtype(self.dtype)
+            if not x.is_cuda:
+                raise TypeError("torch inputs must be CUDA tensors (use NumPy arrays for host data)")
+            if x.dtype != tdt:
+                x = x.to(tdt)
+            if x.shape[0] != nin:
+                raise ValueError(f"DimensionMismatch: x has {x.shape[0]} rows, operator needs {nin}")
+            nrhs = 1 if x.dim() == 1 else x.shape[1]
+            xm = x if x.dim() == 1 else x.t().contiguous().t()      # column-major storage
+            if x.dim() == 1 and not x.is_contiguous():
+                xm = x.contiguous()
+            if y is None:
+                if not beta_false:
+                    raise ValueError("beta needs an existing y")
+                y = torch.empty((nrhs, nout), dtype=tdt, device=x.device).t() if x.dim() == 2 else \
+                    torch.empty(nout, dtype=tdt, device=x.device)
+            if y.dtype != tdt or y.shape[0] != nout:
+                raise ValueError("DimensionMismatch: y does not match the operator")
+            ldx = xm.stride(1) if xm.dim() == 2 else nin
+            ldy = y.stride(1) if y.dim() == 2 else nout
+            if y.dim() == 2 and (y.stride(0) != 1):
+                raise ValueError("y must be column-major (stride(0) == 1)")
+            st = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
+            L.check(lib.bsm_mul(self._h, _OPS[op], a.ctypes.data_as(c_void_p), b.ctypes.data_as(c_void_p),
+                                int(beta_false), c_void_p(xm.data_ptr()), ldx, c_void_p(y.data_ptr()), ldy,
+                                nrhs, c_void_p(st)))
+            return y
+        x = np.asarray(x)
+        if x.shape[0] != nin:
+            raise ValueError(f"DimensionMismatch: x has {x.shape[0]} rows, operator needs {nin}")
+        nrhs = 1 if x.ndim == 1 else x.shape[1]
+        xm = np.asfortranarray(x, dtype=self.dtype) if x.ndim == 2 else np.ascontiguousarray(x, dtype=self.dtype)
+        if y is None:
+            if not beta_false:
+                raise ValueError("beta needs an existing y")
+            y = np.empty((nout, nrhs), self.dtype, order="F") if x.ndim == 2 else np.empty(nout, self.dtype)
+        if y.dtype != self.dtype or y.shape[0] != nout or (y.ndim == 2 and not y.flags.f_contiguous) or \
+                (y.ndim == 1 and not y.flags.c_contiguous):
+            raise ValueError("DimensionMismatch: y must be a contiguous (column-major) array of the operator's dtype")
+        L.check(lib.bsm_mul_host(self._h, _OPS[op], a.ctypes.data_as(c_void_p), b.ctypes.data_as(c_void_p),
+                                 int(beta_false), xm.ctypes.data_as(c_void_p), nin, y.ctypes.data_as(c_void_p),
+                                 nout, nrhs))
+        return y
+
+
+CONTRIB_DTYPE = np.dtype([("off", np.int64), ("m", np.int32), ("n", np.int32), ("in_set", np.int32),
+                          ("form", np.int32), ("out_len", np.int32), ("block", np.int32)])
+SLICE_DTYPE = np.dtype([("out_set", np.int32), ("r0", np.int32), ("r1", np.int32), ("c_begin", np.int32),
+                        ("c_end", np.int32), ("flags", np.int32), ("scratch_off", np.int64)])
+assert CONTRIB_DTYPE.itemsize == 32 and SLICE_DTYPE.itemsize == 32
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _torch_dtype(dt):
+    import torch
+    return {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+            np.dtype(np.complex128): torch.complex128}[np.dtype(dt)]
+
+
+def _device_of(A) -> DeviceMatrix:
+    if isinstance(A, DeviceMatrix):
+        return A
+    if isinstance(A, AbstractBlockMatrix):
+        return A.device()
+    raise TypeError(f"not a block matrix: {type(A).__name__}")
+
+
+def apply(A, op, x):
+    """y = op(A) * x with LinearMaps' promotion: complex blocks times real x promote x
+    (the reference's own VBCRS tests do this, test/test_vbcrs.jl:34-35); real blocks times complex x
+    are two real right-hand sides."""
+    D = _device_of(A)
+    if _is_torch(x):
+        import torch
+        if x.is_complex() and D.dtype.kind != "c":
+            yr = D.mul(op, x.real.contiguous())
+            yi = D.mul(op, x.imag.contiguous())
+            return torch.complex(yr, yi)
+        return D.mul(op, x)
+    x = np.asarray(x)
+    if np.iscomplexobj(x) and D.dtype.kind != "c":
+        return D.mul(op, np.ascontiguousarray(x.real)) + 1j * D.mul(op, np.ascontiguousarray(x.imag))
+    return D.mul(op, x)
+
+
+def mul_into(y, A, op, x, alpha=True, beta=False):
+    D = _device_of(A)
+    if not _is_torch(x):
+        x = np.asarray(x)
+        if np.iscomplexobj(x) and D.dtype.kind != "c":
+            raise TypeError("mul_: complex x with a real operator needs a complex y; use A * x")
+    return D.mul(op, x, y, alpha, beta)
+
+
+class DeviceAdjoint(_Wrapped):
+    _op = "C"
+
+
+class DeviceTranspose(_Wrapped):
+    _op = "T"

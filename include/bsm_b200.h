@@ -1,0 +1,200 @@
+/* bsm_b200.h — C ABI of libbsm_b200.so: the B200-native replacement for the multiply hot path of
+ * BlockSparseMatrices.jl (v0.3.1). Plain pointers and sizes only; no CUDA/torch types.
+ *
+ * What each entry point replaces (file:line relative to the reference repository):
+ *
+ *   bsm_create_blocksparse   BlockSparseMatrix struct + ctor          src/blockmatrix.jl:26-34, 81-109
+ *   bsm_create_symmetric     SymmetricBlockMatrix struct + ctor       src/symmetricblockmatrix.jl:33-44, 94-126
+ *   bsm_create_vbcrs         VariableBlockCompressedRowStorage struct src/vbcrs.jl:36-43 (already sorted,
+ *                            i.e. the output of the sorting ctor src/vbcrs.jl:78-122)
+ *   bsm_mul                  LinearMaps._unsafe_mul!(y, A|A'|transpose(A), x, α, β) for the three types
+ *                            src/abstractblockmatrix.jl:27-34, src/blockmatrix.jl:225-247,
+ *                            src/symmetricblockmatrix.jl:386-435, src/vbcrs.jl:266-288, 303-354
+ *   bsm_mul_host             the same call with HOST x / y (copies inside) — what `mul!(y, A, x)` on
+ *                            Julia Arrays maps to when the caller holds no device arrays
+ *   bsm_nnz                  SparseArrays.nnz                         src/blockmatrix.jl:208-223,
+ *                            src/symmetricblockmatrix.jl:367-384, src/vbcrs.jl:290-296
+ *   bsm_size                 Base.size                                src/abstractblockmatrix.jl:23-25
+ *
+ * Conventions
+ *   - Indices are 1-based Int64 at this boundary, exactly as Julia holds them; the packer converts
+ *     once to 0-based Int32 device tables.
+ *   - Blocks are column-major (Julia `Matrix{T}`), leading dimension = number of rows.
+ *   - Host block / index pointers are read only during bsm_create_*; the handle owns device copies.
+ *   - Every function returns 0 on success or a negative bsm_status; it never throws or exits.
+ *     bsm_last_error() returns a thread-local message for the last failure.
+ *   - A handle is immutable after creation: bsm_mul may be called concurrently from several host
+ *     threads on different streams.
+ *   - alpha / beta are passed by pointer as ONE element of the matrix dtype.
+ *   - beta_is_false != 0 reproduces Julia's `β = false` strong zero (y is overwritten, NaN/Inf in y
+ *     are not propagated: src/abstractblockmatrix.jl:33, src/blockmatrix.jl:231); beta is then ignored.
+ *   - There is no CPU fallback: without a CUDA device every create/mul call fails with
+ *     BSM_ERR_CUDA.
+ */
+#ifndef BSM_B200_H
+#define BSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bsm_matrix *bsm_handle;
+
+typedef enum { BSM_F32 = 0, BSM_F64 = 1, BSM_C64 = 2 /* ComplexF64 */ } bsm_dtype;
+typedef enum { BSM_OP_N = 0, BSM_OP_T = 1, BSM_OP_C = 2 } bsm_op; /* A, transpose(A), A' */
+typedef enum { BSM_KIND_BLOCKSPARSE = 0, BSM_KIND_SYMMETRIC = 1, BSM_KIND_VBCRS = 2 } bsm_kind;
+
+typedef enum {
+    BSM_OK = 0,
+    BSM_ERR_ARG = -1,     /* bad argument (null pointer, bad dtype/op, index out of range) */
+    BSM_ERR_CUDA = -2,    /* CUDA runtime failure or no device */
+    BSM_ERR_ALLOC = -3,   /* host or device allocation failed */
+    BSM_ERR_UNSUPPORTED = -4
+} bsm_status;
+
+/* Kernel variants (benchmarked against each other; BSM_VARIANT_AUTO picks per plan). */
+typedef enum {
+    BSM_VARIANT_AUTO = 0,
+    BSM_VARIANT_GATHER = 1,  /* owner-computes gather GEMV, direct global loads (two passes over
+                                half-stored symmetric blocks) */
+    BSM_VARIANT_FUSED = 2,   /* symmetric: one pass over each half-stored block, transposed partials
+                                gathered through the transposed index */
+    BSM_VARIANT_COLOR = 3    /* colour-ordered multi-launch (the reference's schedule, for comparison) */
+} bsm_variant;
+
+/* Creation options; pass NULL for defaults. */
+/* device = BSM_DEVICE_NONE builds a host-only handle: the packer runs and every table except the
+ * arena can be exported (packing tests on machines without a GPU); bsm_mul* on it fail with
+ * BSM_ERR_CUDA. */
+#define BSM_DEVICE_NONE (-2)
+
+typedef struct {
+    int32_t device;        /* CUDA device ordinal; -1 = current device; BSM_DEVICE_NONE = host-only */
+    int32_t variant;       /* bsm_variant used by bsm_mul unless overridden by bsm_set_variant */
+    /* Owned output range of this rank's slab (0-based, half-open). Contributions whose outputs
+     * fall outside are dropped; [0, -1) = everything. own_row_* applies to op N (outputs are
+     * rows), own_col_* to op T/C (outputs are columns). */
+    int64_t own_row_lo, own_row_hi;
+    int64_t own_col_lo, own_col_hi;
+    int64_t reserved[4];
+} bsm_options;
+
+void bsm_default_options(bsm_options *opt);
+
+/* BlockSparseMatrix: nb blocks; block b is m[b] x n[b]; its row / column index vectors are
+ * rowidx[rowptr[b] .. rowptr[b+1]) and colidx[colptr[b] .. colptr[b+1]) (pool offsets 0-based,
+ * index VALUES 1-based), with rowptr[b+1]-rowptr[b] == m[b] and colptr[b+1]-colptr[b] == n[b]. */
+int bsm_create_blocksparse(int dtype, int64_t nrows, int64_t ncols, int64_t nb,
+                           const void *const *blocks, const int64_t *m, const int64_t *n,
+                           const int64_t *rowidx, const int64_t *rowptr, const int64_t *colidx,
+                           const int64_t *colptr, const bsm_options *opt, bsm_handle *out);
+
+/* SymmetricBlockMatrix: ndiag square diagonal blocks (dsize[d] x dsize[d], index vector
+ * didx[dptr[d] .. dptr[d+1])) and noff half-stored off-diagonal blocks (om[b] x on[b], row / column
+ * index vectors as above). */
+int bsm_create_symmetric(int dtype, int64_t nrows, int64_t ncols, int64_t ndiag,
+                         const void *const *diag, const int64_t *dsize, const int64_t *didx,
+                         const int64_t *dptr, int64_t noff, const void *const *off,
+                         const int64_t *om, const int64_t *on, const int64_t *rowidx,
+                         const int64_t *rowptr, const int64_t *colidx, const int64_t *colptr,
+                         const bsm_options *opt, bsm_handle *out);
+
+/* VBCRS: nbrows block rows; rowptr (1-based, length nbrows+1, sentinel nb+1), colstart[b] (1-based
+ * first column of block b), rowstart[r] (1-based first row of block row r); block b is m[b] x n[b].
+ * is_transposed (nullable): is_transposed[b] != 0 means blocks[b] points at the PARENT of a lazy
+ * `transpose(parent)` wrapper (parent is n[b] x m[b] column-major) as produced by the
+ * SymmetricBlockMatrix → VBCRS conversion (src/vbcrs.jl:222-264); it is materialised while packing. */
+int bsm_create_vbcrs(int dtype, int64_t nrows, int64_t ncols, int64_t nbrows, int64_t nb,
+                     const int64_t *rowptr, const int64_t *colstart, const int64_t *rowstart,
+                     const void *const *blocks, const int64_t *m, const int64_t *n,
+                     const uint8_t *is_transposed, const bsm_options *opt, bsm_handle *out);
+
+int bsm_destroy(bsm_handle h);
+
+/* y[:, j] = alpha * op(A) * x[:, j] + beta * y[:, j], j < nrhs; x and y are DEVICE pointers of the
+ * matrix dtype, column-major with leading dimensions ldx / ldy (elements). `stream` is a
+ * cudaStream_t cast to void* (NULL = default stream). Asynchronous with respect to the host. */
+int bsm_mul(bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
+            const void *x_dev, int64_t ldx, void *y_dev, int64_t ldy, int64_t nrhs, void *stream);
+
+/* Same with HOST x / y: H2D of x (and of y when beta is used), multiply, D2H of y, then
+ * synchronises. Uses pinned staging buffers owned by the handle (serialised per handle). */
+int bsm_mul_host(bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
+                 const void *x_host, int64_t ldx, void *y_host, int64_t ldy, int64_t nrhs);
+
+int bsm_set_variant(bsm_handle h, int variant);
+
+/* ---- queries ---------------------------------------------------------------------------- */
+int64_t bsm_nnz(bsm_handle h);          /* SparseArrays.nnz semantics (symmetric: 2*off + diag) */
+int64_t bsm_stored_entries(bsm_handle h); /* entries held in the arena (half-stored counted once) */
+int bsm_size(bsm_handle h, int64_t *nrows, int64_t *ncols);
+int bsm_dtype_of(bsm_handle h);
+int bsm_kind_of(bsm_handle h);
+/* Algorithmic bytes / flops of one multiply with nrhs right-hand sides:
+ * bytes = stored*s + (ncols + nrows*(1 + beta_used))*s*nrhs + index_table_bytes. */
+int bsm_work(bsm_handle h, int op, int64_t nrhs, int beta_used, double *bytes, double *flops,
+             double *index_table_bytes);
+/* Number of kernels one bsm_mul launches for `op` with the current variant (nrhs = 1). */
+int bsm_launch_count(bsm_handle h, int op);
+
+/* ---- table export (bit-exact packing checks) ---------------------------------------------- */
+typedef enum {
+    BSM_TAB_ARENA = 0,        /* dtype elements, device arena copied back */
+    BSM_TAB_BLOCK_OFF = 1,    /* int64: element offset of every block in the arena (128-byte aligned) */
+    BSM_TAB_BLOCK_M = 2,      /* int32 */
+    BSM_TAB_BLOCK_N = 3,      /* int32 */
+    BSM_TAB_SET_LEN = 4,      /* int32: index-set table (deduplicated row/column index vectors) */
+    BSM_TAB_SET_START = 5,    /* int32: 0-based first index if the set is a contiguous range, else -1 */
+    BSM_TAB_SET_POOL_OFF = 6, /* int64: offset into the index pool (only if SET_START < 0) */
+    BSM_TAB_POOL = 7,         /* int32: 0-based indices */
+    /* per-plan tables (plan 0 = op N, plan 1 = op T/C): */
+    BSM_TAB_CONTRIB = 8,      /* bsm_contrib records, grouped by output segment */
+    BSM_TAB_SLICE = 9,        /* bsm_slice records (work items) */
+    BSM_TAB_GATHER_ROWS = 10, /* int32: rows finalised by the gather pass (bit 31: already written) */
+    BSM_TAB_GATHER_PTR = 11,  /* int64 */
+    BSM_TAB_GATHER_POS = 12,  /* int64: positions in the partial-sum scratch */
+    BSM_TAB_GROUP_PTR = 13,   /* int64: CSR over contributions per output segment ("block-row pointer";
+                                 for plan 1 this is the transposed index) */
+    BSM_TAB_GROUP_SET = 14    /* int32: index-set id of every output segment */
+} bsm_table;
+
+/* 32-byte device records (exported verbatim). */
+typedef struct {
+    int64_t off;       /* arena element offset of the block */
+    int32_t m, n;      /* block is m x n, column-major, ld = m */
+    int32_t in_set;    /* index set gathered from x */
+    int32_t form;      /* 0: y[out] += op(B) x[in] along block rows ("N-form");
+                          1: y[out] += op(B)^T x[in] along block columns ("T-form") */
+    int32_t out_len;   /* outputs this block covers inside its segment (m or n) */
+    int32_t block;     /* block id */
+} bsm_contrib;
+
+typedef struct {
+    int32_t out_set;     /* index set of the output segment */
+    int32_t r0, r1;      /* output sub-range [r0, r1) of the segment handled by this work item */
+    int32_t c_begin, c_end; /* contributions [c_begin, c_end) */
+    int32_t flags;       /* bit0: direct (writes y), else partial sums to scratch; bit1: vector loads ok */
+    int64_t scratch_off; /* element offset of the partial vector when not direct */
+} bsm_slice;
+
+int64_t bsm_table_count(bsm_handle h, int table, int plan); /* number of elements/records, <0 on error */
+int bsm_table_copy(bsm_handle h, int table, int plan, void *dst, int64_t dst_bytes);
+
+/* ---- device memory helpers for callers without a CUDA array package ------------------------ */
+int bsm_device_count(int *count);
+int bsm_malloc(int device, size_t bytes, void **dev_ptr);
+int bsm_free(int device, void *dev_ptr);
+int bsm_memcpy_h2d(void *dev_dst, const void *host_src, size_t bytes);
+int bsm_memcpy_d2h(void *host_dst, const void *dev_src, size_t bytes);
+int bsm_synchronize(int device);
+
+const char *bsm_last_error(void);
+const char *bsm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSM_B200_H */

@@ -1,0 +1,205 @@
+"""Host logic on machines without a GPU: the packer's plan (host-only handle, device = BSM_DEVICE_NONE)
+executed by the NumPy plan interpreter must reproduce the oracle for every type / op, including
+overlapping blocks, repeated indices, uncovered rows and slab-restricted plans."""
+import numpy as np
+import pytest
+
+import bsm_b200 as B
+from bsm_b200 import _lib as L
+from oracle import oracle_np as O
+from plan_interp import run_plan
+from test_oracle import leaf_contiguous
+
+OPS = ["N", "T", "C"]
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def host_only(A, **kw):
+    return A.device(device=L.DEVICE_NONE, **kw)
+
+
+@pytest.fixture(scope="module", params=["cuboid", "sphere"])
+def fixture(request):
+    return O.load_golden_sbm(request.param)
+
+
+@pytest.mark.parametrize("op", OPS)
+def test_sbm_plan(fixture, op):
+    A = fixture
+    P = B.SymmetricBlockMatrix(A.diagonals, A.diagonalindices, A.offdiagonals, A.rowindices, A.colindices, A.size)
+    D = host_only(P)
+    assert D.nnz() == O.nnz_sbm(A) == B.nnz(P)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(A.size[1]) + 1j * rng.standard_normal(A.size[1])
+    y0 = rng.standard_normal(A.size[0]) + 1j * rng.standard_normal(A.size[0])
+    assert rel(run_plan(P, D, op, x), O.mul_sbm(A, x, op)) < 1e-13
+    assert rel(run_plan(P, D, op, x, 1j, 2j, False, y0.copy()), O.mul_sbm(A, x, op, 1j, 2j, False, y0.copy())) < 1e-13
+    # the leaf segments own their rows: diagonal + forward off-diagonal contributions are direct
+    sl = D.table(L.TAB_SLICE, 0)
+    assert (sl["flags"] & 1).sum() > 0
+
+
+@pytest.mark.parametrize("op", OPS)
+def test_bsm_plan(fixture, op):
+    A = O.sbm_to_bsm(fixture)
+    P = B.BlockSparseMatrix(A.blocks, A.rowindices, A.colindices, A.size)
+    D = host_only(P)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(A.size[1]) + 1j * rng.standard_normal(A.size[1])
+    assert rel(run_plan(P, D, op, x), O.mul_bsm(A, x, op)) < 1e-13
+
+
+@pytest.mark.parametrize("op", OPS)
+def test_vbcrs_plan(fixture, op):
+    A = leaf_contiguous(fixture)
+    Ps = B.SymmetricBlockMatrix(A.diagonals, A.diagonalindices, A.offdiagonals, A.rowindices, A.colindices, A.size)
+    V = B.VariableBlockCompressedRowStorage(Ps)
+    OV = O.vbcrs_from_sbm(A)
+    # structure of the sorting constructor / conversion is bit-exact vs the oracle's literal loops
+    assert np.array_equal(V.rowptr, OV.rowptr)
+    assert np.array_equal(V.colindices, OV.colindices)
+    assert np.array_equal(V.rowindices, OV.rowindices)
+    assert all(np.array_equal(a, b) for a, b in zip(V.blocks, OV.blocks))
+    D = host_only(V)
+    assert D.nnz() == O.nnz_vbcrs(OV)
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(A.size[1]) + 0j
+    assert rel(run_plan(V, D, op, x), O.mul_vbcrs(OV, x, op)) < 1e-13
+    # most segments own their rows (runs spanning two adjacent leaves overlap and go through scratch)
+    for plan in (0, 1):
+        assert np.mean(D.table(L.TAB_SLICE, plan)["flags"] & 1) > 0.5
+
+
+def random_bsm(rng, nrows, ncols, nb, dtype, contiguous=False, maxdim=9):
+    blocks, rows, cols = [], [], []
+    for _ in range(nb):
+        m, n = rng.integers(1, maxdim, 2)
+        if contiguous:
+            r0 = rng.integers(1, nrows - m + 2)
+            c0 = rng.integers(1, ncols - n + 2)
+            r, c = np.arange(r0, r0 + m), np.arange(c0, c0 + n)
+        else:
+            r = rng.integers(1, nrows + 1, m)      # repeated indices allowed
+            c = rng.integers(1, ncols + 1, n)
+        b = rng.standard_normal((m, n))
+        if np.dtype(dtype).kind == "c":
+            b = b + 1j * rng.standard_normal((m, n))
+        blocks.append(np.asfortranarray(b.astype(dtype)))
+        rows.append(r.astype(np.int64))
+        cols.append(c.astype(np.int64))
+    return blocks, rows, cols
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+@pytest.mark.parametrize("contiguous", [False, True])
+def test_overlapping_and_uncovered(dtype, contiguous):
+    rng = np.random.default_rng(3)
+    blocks, rows, cols = random_bsm(rng, 40, 33, 25, dtype, contiguous)
+    A = O.OBSM(blocks, rows, cols, (40, 33))
+    P = B.BlockSparseMatrix(blocks, rows, cols, (40, 33))
+    D = host_only(P)
+    tol = 1e-5 if dtype == np.float32 else 1e-13
+    for op in OPS:
+        nin = 33 if op == "N" else 40
+        x = rng.standard_normal(nin).astype(dtype)
+        y0 = rng.standard_normal(73 - nin).astype(dtype)
+        ref = O.mul_bsm(A, x.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64), op)
+        assert rel(run_plan(P, D, op, x), ref) < tol
+        ref5 = O.mul_bsm(A, x, op, 0.5, -1.5, False, y0.copy())
+        assert rel(run_plan(P, D, op, x, 0.5, -1.5, False, y0.copy()), ref5) < tol
+
+
+def test_tall_and_wide_blocks_are_sliced():
+    rng = np.random.default_rng(4)
+    blocks = [np.asfortranarray(rng.standard_normal((300, 7))), np.asfortranarray(rng.standard_normal((5, 700))),
+              np.asfortranarray(rng.standard_normal((300, 300)))]
+    rows = [np.arange(1, 301), np.arange(301, 306), np.arange(1, 301)]
+    cols = [np.arange(1, 8), np.arange(1, 701), np.arange(401, 701)]
+    A = O.OBSM(blocks, rows, cols, (305, 700))
+    P = B.BlockSparseMatrix(blocks, rows, cols, (305, 700))
+    D = host_only(P)
+    for op in OPS:
+        x = rng.standard_normal(700 if op == "N" else 305)
+        assert rel(run_plan(P, D, op, x), O.mul_bsm(A, x, op)) < 1e-13
+    sl = D.table(L.TAB_SLICE, 0)
+    assert np.all(sl["r1"] - sl["r0"] <= 128) and len(sl) >= 4
+
+
+def test_clean_vbcrs_is_single_launch():
+    rng = np.random.default_rng(8)
+    tiles = np.cumsum(np.r_[1, rng.integers(3, 9, 12)])
+    mats, rs, cs = [], [], []
+    for i in range(12):
+        for j in (i, (i + 1) % 12, (i + 5) % 12):
+            mats.append(rng.standard_normal((tiles[i + 1] - tiles[i], tiles[j + 1] - tiles[j])))
+            rs.append(tiles[i])
+            cs.append(tiles[j])
+    n = tiles[-1] - 1
+    V = B.VariableBlockCompressedRowStorage(mats, rs, cs, (n, n))
+    D = host_only(V)
+    for plan in (0, 1):
+        assert np.all(D.table(L.TAB_SLICE, plan)["flags"] & 1)
+        assert D.table(L.TAB_GATHER_ROWS, plan).size == 0
+    assert D.launch_count("N") == 1 and D.launch_count("T") == 1
+    OV = O.vbcrs_from_blocks(mats, rs, cs, (n, n))
+    for op in OPS:
+        x = rng.standard_normal(n)
+        assert rel(run_plan(V, D, op, x), O.mul_vbcrs(OV, x, op)) < 1e-13
+
+
+def test_vbcrs_variable_heights_and_shared_starts():
+    # blocks of one block row with different heights; two block rows overlapping in rows
+    rng = np.random.default_rng(5)
+    mats = [rng.standard_normal((4, 3)), rng.standard_normal((6, 2)), rng.standard_normal((5, 5)),
+            rng.standard_normal((3, 3))]
+    rs, cs = [1, 1, 4, 9], [1, 6, 2, 9]
+    V = B.VariableBlockCompressedRowStorage(mats, rs, cs, (12, 12))
+    OV = O.vbcrs_from_blocks(mats, rs, cs, (12, 12))
+    D = host_only(V)
+    for op in OPS:
+        x = rng.standard_normal(12)
+        assert rel(run_plan(V, D, op, x), O.mul_vbcrs(OV, x, op)) < 1e-13
+
+
+@pytest.mark.parametrize("op", OPS)
+def test_slab_plans_partition_the_product(fixture, op):
+    """Row-slab plans (own_rows / own_cols): every rank writes only its slice, together they give y."""
+    A = fixture
+    P = B.SymmetricBlockMatrix(A.diagonals, A.diagonalindices, A.offdiagonals, A.rowindices, A.colindices, A.size)
+    n = A.size[0]
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    ref = O.mul_sbm(A, x, op)
+    cuts = [0, n // 3, 2 * n // 3 + 5, n]
+    y = np.zeros(n, np.complex128)
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        D = host_only(P, own_rows=(lo, hi), own_cols=(lo, hi))
+        run_plan(P, D, op, x, y=y, own=(lo, hi))
+    assert rel(y, ref) < 1e-13
+
+
+def test_errors():
+    b = [np.ones((2, 2))]
+    with pytest.raises(L.BsmError):      # index out of range
+        host_only(B.BlockSparseMatrix(b, [np.array([1, 5])], [np.array([1, 2])], (3, 3)))
+    with pytest.raises(L.BsmError):      # size mismatch
+        host_only(B.BlockSparseMatrix(b, [np.array([1, 2, 3])], [np.array([1, 2])], (3, 3)))
+    with pytest.raises(IndexError):      # empty VBCRS throws in the reference too
+        B.VariableBlockCompressedRowStorage([], [], [], (1, 1))
+    D = host_only(B.BlockSparseMatrix(b, [np.array([1, 2])], [np.array([1, 2])], (3, 3)))
+    with pytest.raises(L.BsmError):      # no CPU fallback
+        D.mul("N", np.ones(3))
+
+
+def test_abi_exports_every_declared_symbol():
+    import re
+    from pathlib import Path
+    hdr = (Path(__file__).resolve().parent.parent / "include" / "bsm_b200.h").read_text()
+    declared = set(re.findall(r"\b(bsm_[a-z0-9_]+)\s*\(", hdr))
+    lib = L.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == {n for n, _, _ in L.SIGNATURES}
