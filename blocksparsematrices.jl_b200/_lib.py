@@ -52,6 +52,8 @@ SIGNATURES = [
     ("bsm_mul_host", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p,
                              c_int64, c_int64]),
     ("bsm_set_variant", c_int, [c_void_p, c_int]),
+    ("bsm_set_profiling", c_int, [c_void_p, c_int]),
+    ("bsm_get_profile", c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     ("bsm_nnz", c_int64, [c_void_p]),
     ("bsm_stored_entries", c_int64, [c_void_p]),
     ("bsm_size", c_int, [c_void_p, _P64, _P64]),

@@ -82,6 +82,9 @@ struct bsm_matrix {
     void *hx = nullptr, *hy = nullptr;
     int64_t hx_bytes = 0, hy_bytes = 0;
     cudaStream_t host_stream = nullptr;
+    // benchmarking: events around the kernels of the last bsm_mul
+    bool profiling = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -282,10 +285,13 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
         a.nslices = (int32_t)HP.slices.size();
         a.beta_false = beta_is_false ? 1 : 0;
         a.conj = (op == BSM_OP_C && sizeof(T) == 16) ? 1 : 0;
+        const bool prof = A->profiling && nrhs == 1;
+        if (prof) CUDA_TRY(cudaEventRecord(A->ev[0], st));
         if (a.nslices > 0) {
             gather_gemv_kernel<T, VMAX><<<a.nslices, kThreads, 0, st>>>(a);
             CUDA_TRY(cudaGetLastError());
         }
+        if (prof) CUDA_TRY(cudaEventRecord(A->ev[1], st));
         const int64_t ng = (int64_t)HP.gather_rows.size();
         if (ng > 0) {
             FinalizeArgs<T> f;
@@ -301,6 +307,7 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             gather_finalize_kernel<T><<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(f);
             CUDA_TRY(cudaGetLastError());
         }
+        if (prof) CUDA_TRY(cudaEventRecord(A->ev[2], st));
     }
     if (scratch) CUDA_TRY(cudaFreeAsync(scratch, st));
     return 0;
@@ -537,6 +544,8 @@ int bsm_destroy(bsm_handle h) {
     if (h->hx) cudaFree(h->hx);
     if (h->hy) cudaFree(h->hy);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    for (int i = 0; i < 3; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
     return 0;
 }
@@ -545,6 +554,29 @@ int bsm_set_variant(bsm_handle h, int variant) {
     if (int rc = check_handle(h)) return rc;
     if (variant < BSM_VARIANT_AUTO || variant > BSM_VARIANT_COLOR) return fail(BSM_ERR_ARG, "bad variant");
     h->variant = variant;
+    return 0;
+}
+
+int bsm_set_profiling(bsm_handle h, int on) {
+    if (int rc = check_handle(h)) return rc;
+    if (h->device == BSM_DEVICE_NONE) return fail(BSM_ERR_CUDA, "host-only handle");
+    DeviceGuard g(h->device);
+    if (on && !h->ev[0])
+        for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
+    h->profiling = on != 0;
+    return 0;
+}
+
+int bsm_get_profile(bsm_handle h, double *main_ms, double *finalize_ms) {
+    if (int rc = check_handle(h)) return rc;
+    if (!h->profiling || !h->ev[0]) return fail(BSM_ERR_ARG, "profiling is off");
+    DeviceGuard g(h->device);
+    CUDA_TRY(cudaEventSynchronize(h->ev[2]));
+    float a = 0.f, b = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+    if (main_ms) *main_ms = a;
+    if (finalize_ms) *finalize_ms = b;
     return 0;
 }
 

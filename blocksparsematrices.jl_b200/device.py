@@ -161,6 +161,15 @@ class DeviceMatrix:
     def launch_count(self, op="N") -> int:
         return int(L.lib().bsm_launch_count(self._h, _OPS[op]))
 
+    def set_profiling(self, on: bool):
+        L.check(L.lib().bsm_set_profiling(self._h, int(on)))
+
+    def profile(self):
+        """(main kernel ms, gather/finalize kernel ms) of the most recent multiply."""
+        a, b = c_double(), c_double()
+        L.check(L.lib().bsm_get_profile(self._h, byref(a), byref(b)))
+        return a.value, b.value
+
     def set_variant(self, variant: int):
         L.check(L.lib().bsm_set_variant(self._h, variant))
 

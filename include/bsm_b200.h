@@ -127,6 +127,13 @@ int bsm_mul_host(bsm_handle h, int op, const void *alpha, const void *beta, int 
 
 int bsm_set_variant(bsm_handle h, int variant);
 
+/* Per-kernel device timing for roofline reports: when on, bsm_mul brackets each of its kernels with
+ * CUDA events on the launch stream (nrhs = 1 only). bsm_get_profile synchronises on the last
+ * recorded events and returns the milliseconds of the main multiply kernel and of the gather
+ * (finalize) kernel of the most recent bsm_mul. Not thread-safe; benchmarking only. */
+int bsm_set_profiling(bsm_handle h, int on);
+int bsm_get_profile(bsm_handle h, double *main_ms, double *finalize_ms);
+
 /* ---- queries ---------------------------------------------------------------------------- */
 int64_t bsm_nnz(bsm_handle h);          /* SparseArrays.nnz semantics (symmetric: 2*off + diag) */
 int64_t bsm_stored_entries(bsm_handle h); /* entries held in the arena (half-stored counted once) */

@@ -1,0 +1,192 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (bsm_create_* / bsm_mul / bsm_mul_host).
+
+Restates the reference's test battery (/root/reference/test/test_blockmatrix.jl:34-106,
+test/test_symmetricblockmatrix.jl:45-107, test/test_vbcrs.jl:17-90) with the oracle in the role of
+`sparse(A) * x`. Tolerances (north_star): rel ||dy||_2/||y||_2 <= 1e-12 for Float64 / ComplexF64,
+<= 1e-5 for Float32; packing is bit-exact.
+"""
+import numpy as np
+import pytest
+
+import bsm_b200 as B
+from bsm_b200 import _lib as L
+from bsm_b200 import generators as G
+from helpers import TOL, oracle_mul, randx, rel2, to_oracle
+from oracle import oracle_np as O
+from test_oracle import leaf_contiguous
+
+pytestmark = pytest.mark.gpu
+OPS = ["N", "T", "C"]
+
+
+def wrap(A, op):
+    return A if op == "N" else (B.transpose(A) if op == "T" else B.adjoint(A))
+
+
+def battery(A, seed=0, ops=OPS, reps=2):
+    """A*x, A'*x, transpose(A)*x and 5-arg mul! (α=im|0.7, β=2im|-0.4) vs the oracle."""
+    dt = np.dtype(A.dtype)
+    tol = TOL[dt]
+    f64 = dt == np.float32
+    rng = np.random.default_rng(seed)
+    alpha, beta = (1j, 2j) if dt.kind == "c" else (0.7, -0.4)
+    for op in ops:
+        nin = A.size[1] if op == "N" else A.size[0]
+        nout = A.size[0] if op == "N" else A.size[1]
+        for _ in range(reps):
+            x = randx(rng, nin, dt)
+            y = wrap(A, op) * x
+            assert y.dtype == dt and y.shape == (nout,)
+            assert rel2(y, oracle_mul(A, x, op, f64=f64)) < tol, (op, "3-arg")
+            y0 = randx(rng, nout, dt)
+            y5 = B.mul_(y0.copy(), wrap(A, op), x, alpha, beta)
+            assert rel2(y5, oracle_mul(A, x, op, alpha, beta, False, y0.copy(), f64=f64)) < tol, (op, "5-arg")
+
+
+@pytest.fixture(scope="module", params=["cuboid", "sphere"])
+def golden(request):
+    return O.load_golden_sbm(request.param)
+
+
+def test_symmetric_fixture(golden):
+    A = B.SymmetricBlockMatrix(golden.diagonals, golden.diagonalindices, golden.offdiagonals,
+                               golden.rowindices, golden.colindices, golden.size)
+    battery(A)
+    assert A.device().nnz() == B.nnz(A) == B.sparse(A).nnz      # test_symmetricblockmatrix.jl:99-107
+    S = B.sparse(A)
+    assert abs(S - S.T).nnz == 0                                 # issymmetric, :49
+
+
+def test_blocksparse_fixture(golden):
+    E = O.sbm_to_bsm(golden)
+    A = B.BlockSparseMatrix(E.blocks, E.rowindices, E.colindices, E.size)
+    battery(A)
+    assert A.device().nnz() == B.nnz(A) == B.sparse(A).nnz
+
+
+def test_vbcrs_fixture(golden):
+    C = leaf_contiguous(golden)
+    S = B.SymmetricBlockMatrix(C.diagonals, C.diagonalindices, C.offdiagonals, C.rowindices, C.colindices, C.size)
+    E = O.sbm_to_bsm(C)
+    Bm = B.BlockSparseMatrix(E.blocks, E.rowindices, E.colindices, E.size)
+    for V in (B.VariableBlockCompressedRowStorage(S), B.VariableBlockCompressedRowStorage(Bm),
+              B.VariableBlockCompressedRowStorage(Bm.blocks, [r[0] for r in Bm.rowindices],
+                                                  [c[0] for c in Bm.colindices], Bm.size)):
+        assert B.nnz(V) == B.nnz(S) == V.device().nnz()
+        battery(V, reps=1)
+        rng = np.random.default_rng(9)
+        x = rng.standard_normal(V.size[1])                      # real x, complex blocks (test_vbcrs.jl:34)
+        for op in OPS:
+            a, b = wrap(V, op) * x, wrap(S, op) * x
+            assert np.max(np.abs(a - b)) / np.max(np.abs(b)) < 1e-12
+
+
+def test_materialised_matrix(golden):
+    """A[:, :] — one product per unit vector (test_blockmatrix.jl:38-49), as a multi-RHS call."""
+    A = B.SymmetricBlockMatrix(golden.diagonals, golden.diagonalindices, golden.offdiagonals,
+                               golden.rowindices, golden.colindices, golden.size)
+    n = A.size[0]
+    cols = np.arange(0, n, 37)
+    X = np.zeros((n, len(cols)), np.complex128, order="F")
+    X[cols, np.arange(len(cols))] = 1
+    S = B.sparse(A).toarray()
+    assert np.max(np.abs(A * X - S[:, cols])) < 1e-13
+    assert np.max(np.abs(B.adjoint(A) * X - S.conj().T[:, cols])) < 1e-13
+    assert np.max(np.abs(B.transpose(A) * X - S.T[:, cols])) < 1e-13
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+@pytest.mark.parametrize("permuted", [False, True])
+def test_c1_shape(dtype, permuted):
+    A = G.blocksparse_uniform(seed=11, n=2000, nblocks=300, bs=32, dtype=dtype, permuted=permuted)
+    battery(A, reps=1)
+
+
+@pytest.mark.parametrize("permuted", [False, True])
+def test_c2_shape(permuted):
+    A = G.symmetric_nearfield(seed=12, n=12000, k_near=4, permuted=permuted)
+    battery(A, reps=1)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+def test_c3_shape(dtype):
+    A = G.vbcrs_variable(seed=13, n=60000, dtype=dtype)
+    battery(A, reps=1)
+    Bm = G.vbcrs_variable(seed=13, n=60000, dtype=dtype, as_blocksparse=True)
+    x = randx(np.random.default_rng(1), 60000, dtype)
+    assert rel2(A * x, Bm * x) < TOL[np.dtype(dtype)]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_c4_shape(dtype):
+    A = G.blocksparse_large(seed=14, grid=6, bs=1024, density=0.2, dtype=dtype)
+    battery(A, reps=1)
+
+
+def test_odd_sizes_and_overlaps():
+    from test_packing_cpu import random_bsm
+    rng = np.random.default_rng(3)
+    for dtype in (np.float32, np.float64, np.complex128):
+        for contiguous in (False, True):
+            blocks, rows, cols = random_bsm(rng, 400, 333, 120, dtype, contiguous, maxdim=40)
+            battery(B.BlockSparseMatrix(blocks, rows, cols, (400, 333)), reps=1)
+
+
+def test_beta_false_is_strong_zero_and_beta_zero_propagates():
+    A = G.blocksparse_uniform(seed=15, n=640, nblocks=50, bs=32)
+    x = np.ones(640)
+    y = np.full(640, np.nan)
+    out = B.mul_(y, A, x, True, False)
+    assert np.all(np.isfinite(out))
+    y = np.full(640, np.nan)
+    out = B.mul_(y, A, x, 1.0, 0.0)
+    assert np.all(np.isnan(out))
+
+
+def test_arena_and_tables_bit_exact():
+    A = G.symmetric_nearfield(seed=16, n=3000, k_near=3, permuted=True)
+    D = A.device()
+    arena = D.table(L.TAB_ARENA)
+    off = D.table(L.TAB_BLOCK_OFF)
+    blocks = list(A.diagonals) + list(A.offdiagonals)
+    assert np.all((off * arena.itemsize) % 128 == 0)
+    covered = np.zeros(arena.size, bool)
+    for b, o in zip(blocks, off):
+        assert np.array_equal(arena[o:o + b.size], b.reshape(-1, order="F"))     # verbatim, column-major
+        covered[o:o + b.size] = True
+    assert np.all(arena[~covered] == 0)
+    assert D.stored_entries() == sum(b.size for b in blocks)
+    # host-only handle produces the identical tables (same packer, no device)
+    Dh = A.device(device=L.DEVICE_NONE)
+    for t in (L.TAB_BLOCK_OFF, L.TAB_SET_LEN, L.TAB_SET_START, L.TAB_POOL):
+        assert np.array_equal(D.table(t), Dh.table(t))
+    for plan in (0, 1):
+        for t in (L.TAB_CONTRIB, L.TAB_SLICE, L.TAB_GATHER_ROWS, L.TAB_GATHER_PTR, L.TAB_GATHER_POS, L.TAB_GROUP_PTR):
+            assert np.array_equal(D.table(t, plan), Dh.table(t, plan))
+
+
+def test_deterministic_and_torch_device_path():
+    import torch
+    A = G.symmetric_nearfield(seed=17, n=20000, k_near=4)
+    D = A.device()
+    rng = np.random.default_rng(0)
+    x = randx(rng, 20000, np.complex128)
+    xd = torch.from_numpy(x).cuda()
+    y1 = D.mul("N", xd).cpu().numpy()
+    y2 = D.mul("N", xd).cpu().numpy()
+    assert np.array_equal(y1, y2)                      # atomic-free → bitwise reproducible
+    assert np.array_equal(y1, D.mul("N", x))           # host path = device path
+    assert rel2(y1, oracle_mul(A, x, "N")) < 1e-12
+    # multi-RHS through device pointers, column-major X
+    X = torch.randn(20000, 3, dtype=torch.complex128, device="cuda")
+    Y = D.mul("C", X)
+    for j in range(3):
+        assert rel2(Y[:, j].cpu().numpy(), oracle_mul(A, X[:, j].cpu().numpy(), "C")) < 1e-12
+
+
+def test_real_matrix_complex_x_promotes():
+    A = G.vbcrs_variable(seed=18, n=5000)
+    x = randx(np.random.default_rng(2), 5000, np.complex128)
+    y = A * x
+    ref = oracle_mul(A, np.ascontiguousarray(x.real), "N") + 1j * oracle_mul(A, np.ascontiguousarray(x.imag), "N")
+    assert rel2(y, ref) < 1e-12
