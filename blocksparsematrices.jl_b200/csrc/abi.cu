@@ -55,11 +55,13 @@ struct DevBuf {
 
 struct DevPlan {
     DevBuf<bsm_contrib> contrib;
+    DevBuf<int64_t> contrib_toff;
     DevBuf<bsm_slice> slices;
     DevBuf<int32_t> gather_rows;
     DevBuf<int64_t> gather_ptr, gather_pos;
     void release() {
         contrib.release();
+        contrib_toff.release();
         slices.release();
         gather_rows.release();
         gather_ptr.release();
@@ -76,7 +78,7 @@ struct bsm_matrix {
     void *arena = nullptr;
     DevBuf<int32_t> set_len, set_start, pool;
     DevBuf<int64_t> set_pool_off;
-    DevPlan plan[2];
+    DevPlan plan[4];
     // host-pointer path
     std::mutex host_mu;
     void *hx = nullptr, *hy = nullptr;
@@ -199,8 +201,10 @@ int upload_tables(bsm_matrix *A) {
     if (int rc = A->set_start.upload(H.sets.start)) return rc;
     if (int rc = A->set_pool_off.upload(H.sets.pool_off)) return rc;
     if (int rc = A->pool.upload(H.sets.pool)) return rc;
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < 4; ++p) {
+        if (p >= 2 && !H.has_fused) break;
         if (int rc = A->plan[p].contrib.upload(H.plan[p].contrib)) return rc;
+        if (int rc = A->plan[p].contrib_toff.upload(H.plan[p].contrib_toff)) return rc;
         if (int rc = A->plan[p].slices.upload(H.plan[p].slices)) return rc;
         if (int rc = A->plan[p].gather_rows.upload(H.plan[p].gather_rows)) return rc;
         if (int rc = A->plan[p].gather_ptr.upload(H.plan[p].gather_ptr)) return rc;
@@ -210,7 +214,8 @@ int upload_tables(bsm_matrix *A) {
 }
 
 // Shared tail of the three create functions.
-int finish_create(bsm_matrix *A, const std::vector<ContribIR> ir[2], const bsm_options *opt,
+// ir[0], ir[1]: GATHER plans for op N and op T/C; ir[2], ir[3]: FUSED plans (only if H.has_fused).
+int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_options *opt,
                   bsm_handle *out) {
     HostMatrix &H = A->H;
     if (H.nrows >= (1ll << 31) || H.ncols >= (1ll << 31)) {
@@ -228,6 +233,19 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> ir[2], const bsm_o
     }
     std::string err = build_plan(H, ir[0], H.nrows, H.ncols, pp[0], H.plan[0]);
     if (err.empty()) err = build_plan(H, ir[1], H.ncols, H.nrows, pp[1], H.plan[1]);
+    if (H.has_fused) {
+        pp[0].fused = pp[1].fused = true;
+        if (err.empty()) err = build_plan(H, ir[2], H.nrows, H.ncols, pp[0], H.plan[2]);
+        if (err.empty()) err = build_plan(H, ir[3], H.ncols, H.nrows, pp[1], H.plan[3]);
+    }
+    // one-time setup of the stream-ordered pool the scratch vectors come from: keep freed memory cached
+    if (A->device != BSM_DEVICE_NONE) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, A->device) == cudaSuccess) {
+            uint64_t thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     if (!err.empty()) {
         delete A;
         return fail(BSM_ERR_ARG, err);
@@ -255,13 +273,30 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> ir[2], const bsm_o
     return 0;
 }
 
+// GATHER plans are 0/1, FUSED plans 2/3 (symmetric matrices; AUTO picks FUSED when it exists).
+int plan_index(const bsm_matrix *A, int op) {
+    const int base = (op == BSM_OP_N) ? 0 : 1;
+    const bool fused = A->H.has_fused && (A->variant == BSM_VARIANT_AUTO || A->variant == BSM_VARIANT_FUSED);
+    return base + (fused ? 2 : 0);
+}
+
 template <class T>
 int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int beta_is_false,
                const T *x, int64_t ldx, T *y, int64_t ldy, int64_t nrhs, cudaStream_t st) {
-    const int p = (op == BSM_OP_N) ? 0 : 1;
+    const int p = plan_index(A, op);
     const HostPlan &HP = A->H.plan[p];
     const DevPlan &DP = A->plan[p];
     T *scratch = nullptr;
+    const int32_t nfused = (int32_t)HP.n_fused_slices;
+    if (nfused > 0) {
+        static bool attr_done[3] = {false, false, false};
+        const int di = sizeof(T) == 4 ? 0 : sizeof(T) == 8 ? 1 : 2;
+        if (!attr_done[di]) {
+            CUDA_TRY(cudaFuncSetAttribute(sym_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)fused_smem_bytes<T>()));
+            attr_done[di] = true;
+        }
+    }
     if (HP.scratch_elems > 0)
         CUDA_TRY(cudaMallocAsync((void **)&scratch, (size_t)HP.scratch_elems * sizeof(T), st));
     constexpr int VMAX = 16 / (int)sizeof(T);
@@ -269,6 +304,7 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
         MulArgs<T> a;
         a.arena = (const T *)A->arena;
         a.contrib = DP.contrib.p;
+        a.contrib_toff = DP.contrib_toff.p;
         a.slices = DP.slices.p;
         a.set_len = A->set_len.p;
         a.set_start = A->set_start.p;
@@ -287,8 +323,15 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
         a.conj = (op == BSM_OP_C && sizeof(T) == 16) ? 1 : 0;
         const bool prof = A->profiling && nrhs == 1;
         if (prof) CUDA_TRY(cudaEventRecord(A->ev[0], st));
-        if (a.nslices > 0) {
-            gather_gemv_kernel<T, VMAX><<<a.nslices, kThreads, 0, st>>>(a);
+        if (nfused > 0) {
+            sym_fused_kernel<T><<<nfused, kFThreads, fused_smem_bytes<T>(), st>>>(a);
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (a.nslices > nfused) {
+            MulArgs<T> b = a;
+            b.slices = a.slices + nfused;
+            b.nslices = a.nslices - nfused;
+            gather_gemv_kernel<T, VMAX><<<b.nslices, kThreads, 0, st>>>(b);
             CUDA_TRY(cudaGetLastError());
         }
         if (prof) CUDA_TRY(cudaEventRecord(A->ev[1], st));
@@ -405,7 +448,8 @@ int bsm_create_symmetric(int dtype, int64_t nrows, int64_t ncols, int64_t ndiag,
     H.kind = BSM_KIND_SYMMETRIC;
     H.nrows = nrows;
     H.ncols = ncols;
-    std::vector<ContribIR> ir[2];
+    H.has_fused = true;
+    std::vector<ContribIR> ir[4];
     // diagonal sweep (/root/reference/src/symmetricblockmatrix.jl:420-432); emitted first so the
     // leaf segments claim their rows and are written directly
     for (int64_t d = 0; d < ndiag; ++d) {
@@ -422,6 +466,8 @@ int bsm_create_symmetric(int dtype, int64_t nrows, int64_t ncols, int64_t ndiag,
         H.nnz += dsize[d] * dsize[d];
         ir[0].push_back(ContribIR{(int32_t)d, 0, ds, ds, (int32_t)dsize[d]});
         ir[1].push_back(ContribIR{(int32_t)d, 1, ds, ds, (int32_t)dsize[d]});  // transpose(D)/adjoint(D), :225-237
+        ir[2].push_back(ir[0].back());
+        ir[3].push_back(ir[1].back());
     }
     std::vector<int32_t> rs((size_t)noff), cs((size_t)noff);
     for (int64_t b = 0; b < noff; ++b) {
@@ -451,6 +497,19 @@ int bsm_create_symmetric(int dtype, int64_t nrows, int64_t ncols, int64_t ndiag,
         const int32_t blk = (int32_t)(ndiag + b);
         ir[0].push_back(ContribIR{blk, 1, cs[b], rs[b], (int32_t)on[b]});
         ir[1].push_back(ContribIR{blk, 1, cs[b], rs[b], (int32_t)on[b]});
+    }
+    // FUSED plans: both sweeps of a half-stored block from ONE pass over it, whenever its row segment
+    // fits the fused kernel; taller blocks keep the two separate contributions
+    for (int pl = 2; pl < 4; ++pl) {
+        for (int64_t b = 0; b < noff; ++b) {
+            const int32_t blk = (int32_t)(ndiag + b);
+            ContribIR c{blk, 0, rs[b], cs[b], (int32_t)om[b]};
+            if (om[b] <= kFusedMaxRows) c.fuse_tset = cs[b];
+            ir[pl].push_back(c);
+        }
+        for (int64_t b = 0; b < noff; ++b)
+            if (om[b] > kFusedMaxRows)
+                ir[pl].push_back(ContribIR{(int32_t)(ndiag + b), 1, cs[b], rs[b], (int32_t)on[b]});
     }
     return finish_create(A, ir, opt, out);
 }
@@ -669,7 +728,7 @@ int bsm_work(bsm_handle h, int op, int64_t nrhs, int beta_used, double *bytes, d
     if (int rc = check_handle(h)) return rc;
     if (op < BSM_OP_N || op > BSM_OP_C) return fail(BSM_ERR_ARG, "bad op");
     const HostMatrix &H = h->H;
-    const HostPlan &P = H.plan[op == BSM_OP_N ? 0 : 1];
+    const HostPlan &P = H.plan[plan_index(h, op)];
     const double s = dtype_size(H.dtype);
     const double tab = (double)P.contrib.size() * sizeof(bsm_contrib) + (double)P.slices.size() * sizeof(bsm_slice) +
                        (double)H.sets.pool.size() * 4 + (double)H.sets.len.size() * 16 +
@@ -683,8 +742,9 @@ int bsm_work(bsm_handle h, int op, int64_t nrhs, int beta_used, double *bytes, d
 
 int bsm_launch_count(bsm_handle h, int op) {
     if (!h || op < BSM_OP_N || op > BSM_OP_C) return BSM_ERR_ARG;
-    const HostPlan &P = h->H.plan[op == BSM_OP_N ? 0 : 1];
-    return (P.slices.empty() ? 0 : 1) + (P.gather_rows.empty() ? 0 : 1);
+    const HostPlan &P = h->H.plan[plan_index(h, op)];
+    return (P.n_fused_slices > 0 ? 1 : 0) + ((int64_t)P.slices.size() > P.n_fused_slices ? 1 : 0) +
+           (P.gather_rows.empty() ? 0 : 1);
 }
 
 }  // extern "C"
@@ -708,7 +768,7 @@ TabView view(const std::vector<U> &v) {
 TabView table_view(bsm_handle h, int table, int plan, std::vector<int32_t> &tmp32) {
     const HostMatrix &H = h->H;
     TabView t;
-    if (plan < 0 || plan > 1) return t;
+    if (plan < 0 || plan > 3) return t;
     const HostPlan &P = H.plan[plan];
     switch (table) {
     case BSM_TAB_ARENA:
@@ -736,6 +796,7 @@ TabView table_view(bsm_handle h, int table, int plan, std::vector<int32_t> &tmp3
     case BSM_TAB_GATHER_POS: return view(P.gather_pos);
     case BSM_TAB_GROUP_PTR: return view(P.group_ptr);
     case BSM_TAB_GROUP_SET: return view(P.group_set);
+    case BSM_TAB_CONTRIB_TOFF: return view(P.contrib_toff);
     }
     return t;
 }

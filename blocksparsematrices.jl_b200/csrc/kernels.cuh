@@ -98,6 +98,7 @@ template <class T>
 struct MulArgs {
     const T *arena;
     const bsm_contrib *contrib;
+    const int64_t *contrib_toff;
     const bsm_slice *slices;
     const int32_t *set_len;
     const int32_t *set_start;
@@ -199,7 +200,7 @@ __device__ __forceinline__ void slice_body(const MulArgs<T> &a, const bsm_slice 
         const bsm_contrib cb = a.contrib[ci];
         const SetRef in = set_ref(a, cb.in_set);
         const T *blk = a.arena + cb.off;
-        if (cb.form == 0) {
+        if ((cb.form & 1) == 0) {
             // rows [r0, r0+h) ∩ [0, out_len) of every column
             const bool rows_ok = active && (r0 + iv * V) < cb.out_len;
             for (int32_t j0 = 0; j0 < cb.n; j0 += kXsCap) {
@@ -268,6 +269,147 @@ __global__ void __launch_bounds__(kThreads) gather_gemv_kernel(const MulArgs<T> 
         else
             slice_body<T, 1, false>(a, sl, xs, red, accT);
     }
+}
+
+// ---- fused symmetric kernel ---------------------------------------------------------------------
+// One CTA (8 warps) per output segment of <= 256 rows, all of its contributions. Lanes own rows
+// (RPL rows per lane, kept in registers), warps stride over column PAIRS. For a half-stored symmetric
+// off-diagonal block O (rows R = this segment, columns C) ONE pass over the block yields
+//     y[R]  += op(O) x[C]          accumulated in registers, written by this CTA
+//     t[C]   = op(O)^T x[R]        complete per column inside the CTA (two-column shuffle butterfly),
+//                                  stored to scratch and summed into y[C] by gather_finalize_kernel
+// which replaces the two sweeps /root/reference/src/symmetricblockmatrix.jl:394-418 (each streaming all
+// off-diagonal storage) and their colour barriers.
+constexpr int kFThreads = 256;
+constexpr int kFWarps = kFThreads / 32;
+constexpr int kFMaxRows = 256;
+
+template <class T, int RPL, bool CONJ>
+__device__ __forceinline__ void fused_slice(const MulArgs<T> &a, const bsm_slice &sl, T *xs, T *xrs,
+                                            T *red, T *accT) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int32_t L = sl.r1;  // r0 == 0: the whole segment
+    const SetRef out = set_ref(a, sl.out_set);
+    xrs[t] = (t < L) ? a.x[out.at(t)] : El<T>::zero();   // x at the segment's own rows
+    accT[t] = El<T>::zero();
+    T accN[RPL];
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) accN[k] = El<T>::zero();
+
+    for (int32_t ci = sl.c_begin; ci < sl.c_end; ++ci) {
+        const bsm_contrib cb = a.contrib[ci];
+        const SetRef in = set_ref(a, cb.in_set);
+        const T *blk = a.arena + cb.off;
+        if ((cb.form & 1) == 0) {
+            const bool fusedT = (cb.form & 2) != 0;
+            const int64_t toff = fusedT ? a.contrib_toff[ci] : 0;
+            const int32_t m = cb.m;
+            for (int32_t j0 = 0; j0 < cb.n; j0 += kXsCap) {
+                const int32_t cn = min(kXsCap, cb.n - j0);
+                __syncthreads();
+                for (int32_t k = t; k < cn; k += kFThreads) xs[k] = a.x[in.at(j0 + k)];
+                __syncthreads();
+                for (int32_t j = 2 * warp; j < cn; j += 2 * kFWarps) {
+                    const bool hasB = (j + 1) < cn;
+                    const T *cA = blk + (int64_t)(j0 + j) * m;
+                    const T *cB = cA + m;
+                    T vA[RPL], vB[RPL];
+#pragma unroll
+                    for (int k = 0; k < RPL; ++k) {
+                        const int32_t i = lane + 32 * k;
+                        vA[k] = (i < m) ? load_stream<T, 1>(cA + i).v[0] : El<T>::zero();
+                        vB[k] = (hasB && i < m) ? load_stream<T, 1>(cB + i).v[0] : El<T>::zero();
+                    }
+                    const T xA = xs[j];
+                    const T xB = hasB ? xs[j + 1] : El<T>::zero();
+                    T tA = El<T>::zero(), tB = El<T>::zero();
+#pragma unroll
+                    for (int k = 0; k < RPL; ++k) {
+                        const T eA = CONJ ? El<T>::conj(vA[k]) : vA[k];
+                        const T eB = CONJ ? El<T>::conj(vB[k]) : vB[k];
+                        El<T>::fma(accN[k], eA, xA);
+                        El<T>::fma(accN[k], eB, xB);
+                        if (fusedT) {
+                            const T xr = xrs[lane + 32 * k];
+                            El<T>::fma(tA, eA, xr);
+                            El<T>::fma(tB, eB, xr);
+                        }
+                    }
+                    if (fusedT) {
+                        // two-column butterfly: lanes < 16 end up with column A, lanes >= 16 with B
+                        const bool hi = (lane & 16) != 0;
+                        const T send = hi ? tA : tB;
+                        T v = El<T>::add(hi ? tB : tA, El<T>::shfl_xor(send, 16));
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) v = El<T>::add(v, El<T>::shfl_xor(v, o));
+                        if (lane == 0) a.scratch[toff + j0 + j] = v;
+                        if (lane == 16 && hasB) a.scratch[toff + j0 + j + 1] = v;
+                    }
+                }
+            }
+        } else {
+            // T-form contribution owned by this segment (transpose(D) / adjoint(D) of a diagonal block)
+            const int32_t hc = min(L, cb.out_len);
+            for (int32_t i0 = 0; i0 < cb.m; i0 += kXsCap) {
+                const int32_t cm = min(kXsCap, cb.m - i0);
+                __syncthreads();
+                for (int32_t k = t; k < cm; k += kFThreads) xs[k] = a.x[in.at(i0 + k)];
+                __syncthreads();
+                for (int32_t jj = warp; jj < hc; jj += kFWarps) {
+                    const T s = tform_column<T, 1, CONJ>(blk + (int64_t)jj * cb.m + i0, cm, lane, xs);
+                    if (lane == 0) accT[jj] = El<T>::add(accT[jj], s);
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) red[warp * kFMaxRows + k * 32 + lane] = accN[k];
+    __syncthreads();
+    if (t < L) {
+        T tot = accT[t];
+#pragma unroll
+        for (int w = 0; w < kFWarps; ++w) tot = El<T>::add(tot, red[w * kFMaxRows + t]);
+        if (sl.flags & 1) {
+            const int32_t row = out.at(t);
+            T v = El<T>::mul(a.alpha, tot);
+            if (!a.beta_false) v = El<T>::add(v, El<T>::mul(a.beta, a.y[row]));
+            a.y[row] = v;
+        } else {
+            a.scratch[sl.scratch_off + t] = tot;
+        }
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kFThreads, 2) sym_fused_kernel(const MulArgs<T> a) {
+    extern __shared__ __align__(16) unsigned char fsm[];
+    T *xs = reinterpret_cast<T *>(fsm);
+    T *xrs = xs + kXsCap;
+    T *accT = xrs + kFMaxRows;
+    T *red = accT + kFMaxRows;  // [kFWarps][kFMaxRows]
+    const bsm_slice sl = a.slices[blockIdx.x];
+    const int32_t L = sl.r1;
+    if (a.conj) {
+        if (L <= 64)
+            fused_slice<T, 2, true>(a, sl, xs, xrs, red, accT);
+        else if (L <= 128)
+            fused_slice<T, 4, true>(a, sl, xs, xrs, red, accT);
+        else
+            fused_slice<T, 8, true>(a, sl, xs, xrs, red, accT);
+    } else {
+        if (L <= 64)
+            fused_slice<T, 2, false>(a, sl, xs, xrs, red, accT);
+        else if (L <= 128)
+            fused_slice<T, 4, false>(a, sl, xs, xrs, red, accT);
+        else
+            fused_slice<T, 8, false>(a, sl, xs, xrs, red, accT);
+    }
+}
+
+template <class T>
+constexpr size_t fused_smem_bytes() {
+    return sizeof(T) * (size_t)(kXsCap + 2 * kFMaxRows + kFWarps * kFMaxRows);
 }
 
 template <class T>

@@ -87,32 +87,43 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
     P.out_dim = out_dim;
     P.in_dim = in_dim;
 
-    // 1. groups in order of first appearance of their output set; drop groups with no owned output
+    // 1. groups in order of first appearance of their output set; a group is dropped when neither
+    //    its own rows nor the rows of a fused transposed partial of one of its blocks are owned
+    std::vector<int8_t> owned_cache(S.len.size(), -1);
+    auto has_owned = [&](int32_t set) -> bool {
+        if (owned_cache[set] < 0) {
+            bool any = false;
+            for (int64_t k = 0; k < S.len[set] && !any; ++k) {
+                const int64_t r = S.at(set, k);
+                any = (r >= own_lo && r < own_hi);
+            }
+            owned_cache[set] = any ? 1 : 0;
+        }
+        return owned_cache[set] == 1;
+    };
     std::vector<int32_t> group_of_set(S.len.size(), -1);
+    std::vector<uint8_t> set_needed(S.len.size(), 0);
+    for (size_t c = 0; c < ir.size(); ++c) {
+        const int32_t os = ir[c].out_set;
+        if (os < 0 || (size_t)os >= S.len.size()) return "bad output set";
+        if (has_owned(os) || (ir[c].fuse_tset >= 0 && has_owned(ir[c].fuse_tset))) set_needed[os] = 1;
+    }
     std::vector<int32_t> gset;
     std::vector<std::vector<int32_t>> members;
     for (size_t c = 0; c < ir.size(); ++c) {
         const int32_t os = ir[c].out_set;
-        if (os < 0 || (size_t)os >= S.len.size()) return "bad output set";
+        if (!set_needed[os]) continue;
         if (group_of_set[os] == -1) {
-            bool any = false;
-            for (int64_t k = 0; k < S.len[os] && !any; ++k) {
-                const int64_t r = S.at(os, k);
-                any = (r >= own_lo && r < own_hi);
-            }
-            if (!any) {
-                group_of_set[os] = -2;  // dropped
-            } else {
-                group_of_set[os] = (int32_t)gset.size();
-                gset.push_back(os);
-                members.emplace_back();
-            }
+            group_of_set[os] = (int32_t)gset.size();
+            gset.push_back(os);
+            members.emplace_back();
         }
-        if (group_of_set[os] >= 0) members[group_of_set[os]].push_back((int32_t)c);
+        members[group_of_set[os]].push_back((int32_t)c);
     }
     const size_t G = gset.size();
 
     // 2. contributions grouped (stable), CSR pointer = block-row pointer / transposed index
+    std::vector<int32_t> contrib_tset;
     P.group_ptr.assign(G + 1, 0);
     P.group_set.assign(gset.begin(), gset.end());
     for (size_t g = 0; g < G; ++g) {
@@ -125,9 +136,14 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
             d.m = b.m;
             d.n = b.n;
             d.in_set = ci.in_set;
-            d.form = ci.form;
+            d.form = ci.form | (ci.fuse_tset >= 0 ? kFormFusedT : 0);
             d.out_len = ci.out_len;
             d.block = ci.block;
+            if (ci.fuse_tset >= 0) {
+                if (ci.form != 0 || !pp.fused || S.len[gset[g]] > kFusedMaxRows || S.len[ci.fuse_tset] < b.n)
+                    return "bad fused contribution";
+            }
+            contrib_tset.push_back(ci.fuse_tset);
             if (ci.out_len > S.len[gset[g]]) return "contribution longer than its output segment";
             if (S.len[ci.in_set] < (ci.form == 0 ? b.n : b.m)) return "input set shorter than block";
             P.contrib.push_back(d);
@@ -175,6 +191,21 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
             if (P.contrib[c].m % V != 0) vec_ok = false;
         }
         if (L % V != 0) vec_ok = false;
+        if (pp.fused && L <= kFusedMaxRows) {
+            // one work item for the whole segment: the fused kernel keeps all its rows in registers
+            Tmp t;
+            t.s.out_set = gset[g];
+            t.s.r0 = 0;
+            t.s.r1 = (int32_t)L;
+            t.s.c_begin = (int32_t)P.group_ptr[g];
+            t.s.c_end = (int32_t)P.group_ptr[g + 1];
+            t.s.flags = (P.group_direct[g] ? kSliceDirect : 0) | kSliceFused;
+            t.s.scratch_off = 0;
+            t.work = W;
+            t.order = (int64_t)tmp.size();
+            tmp.push_back(t);
+            continue;
+        }
         int64_t pieces = (L + kMaxSliceHeight - 1) / kMaxSliceHeight;
         const int64_t by_work = (W + pp.work_target_bytes - 1) / pp.work_target_bytes;
         const int64_t max_pieces = std::max<int64_t>(1, L / hmin);
@@ -204,6 +235,14 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
             scratch += t.s.r1 - t.s.r0;
         }
     }
+    // fused transposed partials: one vector of n entries per fused contribution
+    P.contrib_toff.assign(P.contrib.size(), -1);
+    for (size_t c = 0; c < P.contrib.size(); ++c) {
+        if (contrib_tset[c] >= 0) {
+            P.contrib_toff[c] = scratch;
+            scratch += P.contrib[c].n;
+        }
+    }
     P.scratch_elems = scratch;
 
     // 5. gather lists: every owned row that is not claimed by a direct group, or that receives
@@ -213,6 +252,13 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
         if (t.s.flags & kSliceDirect) continue;
         for (int64_t k = t.s.r0; k < t.s.r1; ++k) {
             const int64_t r = S.at(t.s.out_set, k);
+            if (r >= own_lo && r < own_hi) cnt[(size_t)r + 1]++;
+        }
+    }
+    for (size_t c = 0; c < P.contrib.size(); ++c) {
+        if (contrib_tset[c] < 0) continue;
+        for (int64_t k = 0; k < P.contrib[c].n; ++k) {
+            const int64_t r = S.at(contrib_tset[c], k);
             if (r >= own_lo && r < own_hi) cnt[(size_t)r + 1]++;
         }
     }
@@ -236,11 +282,26 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
         }
     }
 
-    // 6. schedule: heaviest slices first (stable)
-    std::stable_sort(tmp.begin(), tmp.end(),
-                     [](const Tmp &a, const Tmp &b) { return a.work > b.work; });
+    for (size_t c = 0; c < P.contrib.size(); ++c) {
+        if (contrib_tset[c] < 0) continue;
+        for (int64_t k = 0; k < P.contrib[c].n; ++k) {
+            const int64_t r = S.at(contrib_tset[c], k);
+            if (r >= own_lo && r < own_hi)
+                P.gather_pos[(size_t)fill[(size_t)rowslot[(size_t)r]]++] = P.contrib_toff[c] + k;
+        }
+    }
+
+    // 6. schedule: fused slices first, heaviest first inside each class (stable)
+    std::stable_sort(tmp.begin(), tmp.end(), [](const Tmp &a, const Tmp &b) {
+        const int fa = (a.s.flags & kSliceFused) != 0, fb = (b.s.flags & kSliceFused) != 0;
+        if (fa != fb) return fa > fb;
+        return a.work > b.work;
+    });
     P.slices.reserve(tmp.size());
-    for (const auto &t : tmp) P.slices.push_back(t.s);
+    for (const auto &t : tmp) {
+        P.slices.push_back(t.s);
+        if (t.s.flags & kSliceFused) P.n_fused_slices++;
+    }
     return std::string();
 }
 

@@ -29,6 +29,10 @@ static_assert(sizeof(bsm_slice) == 32, "bsm_slice must be 32 bytes");
 
 constexpr int kSliceDirect = 1;
 constexpr int kSliceVecOk = 2;
+constexpr int kSliceFused = 4;          // handled by sym_fused_kernel (whole segment, <= kFusedMaxRows rows)
+constexpr int kFusedMaxRows = 256;
+constexpr int kFormT = 1;               // bsm_contrib.form bit0: T-form
+constexpr int kFormFusedT = 2;          // bit1: also emits the transposed partial of the same block
 constexpr int kMaxSliceHeight = 128;   // outputs per work item (one CTA of 128 threads)
 constexpr int64_t kArenaAlignBytes = 128;
 
@@ -67,6 +71,8 @@ struct ContribIR {
     int32_t out_set;   // output segment (group key)
     int32_t in_set;
     int32_t out_len;
+    int32_t fuse_tset = -1;  // >= 0: one pass over the block also yields y[fuse_tset] += op(B)^T x[out_set]
+                             // (half-stored symmetric off-diagonal block); delivered through scratch
 };
 
 struct HostPlan {
@@ -74,7 +80,9 @@ struct HostPlan {
     std::vector<int64_t> group_ptr;     // CSR over contrib
     std::vector<int32_t> group_set;
     std::vector<uint8_t> group_direct;
-    std::vector<bsm_slice> slices;      // sorted by decreasing work
+    std::vector<int64_t> contrib_toff;  // scratch offset of the fused transposed partial, -1 if none
+    std::vector<bsm_slice> slices;      // fused slices first, each class sorted by decreasing work
+    int64_t n_fused_slices = 0;
     std::vector<int32_t> gather_rows;
     std::vector<int64_t> gather_ptr;
     std::vector<int64_t> gather_pos;
@@ -93,12 +101,16 @@ struct HostMatrix {
     std::vector<int64_t> block_off;    // element offsets, 128-byte aligned
     int64_t arena_elems = 0;           // including tail slack
     IndexSets sets;
-    HostPlan plan[2];
+    // plan[0], plan[1]: GATHER variant for op N, op T/C. plan[2], plan[3]: FUSED variant (symmetric
+    // matrices only; empty otherwise).
+    HostPlan plan[4];
+    bool has_fused = false;
 };
 
 struct PlanParams {
     int64_t own_lo = 0, own_hi = -1;   // owned output range, hi < 0: everything
     int64_t work_target_bytes = 512 << 10;
+    bool fused = false;                // segments of <= kFusedMaxRows rows go to the fused kernel, unsplit
 };
 
 // Lays the blocks out in the arena (fills block_off, arena_elems, stored).

@@ -181,7 +181,8 @@ class DeviceMatrix:
             raise L.BsmError(cnt, "unknown table")
         if table == L.TAB_ARENA:
             dt = self.dtype
-        elif table in (L.TAB_BLOCK_OFF, L.TAB_SET_POOL_OFF, L.TAB_GATHER_PTR, L.TAB_GATHER_POS, L.TAB_GROUP_PTR):
+        elif table in (L.TAB_BLOCK_OFF, L.TAB_SET_POOL_OFF, L.TAB_GATHER_PTR, L.TAB_GATHER_POS, L.TAB_GROUP_PTR,
+                       L.TAB_CONTRIB_TOFF):
             dt = np.dtype(np.int64)
         elif table == L.TAB_CONTRIB:
             dt = CONTRIB_DTYPE

@@ -157,7 +157,8 @@ typedef enum {
     BSM_TAB_SET_START = 5,    /* int32: 0-based first index if the set is a contiguous range, else -1 */
     BSM_TAB_SET_POOL_OFF = 6, /* int64: offset into the index pool (only if SET_START < 0) */
     BSM_TAB_POOL = 7,         /* int32: 0-based indices */
-    /* per-plan tables (plan 0 = op N, plan 1 = op T/C): */
+    /* per-plan tables (GATHER variant: plan 0 = op N, plan 1 = op T/C; FUSED variant, symmetric
+     * matrices only: plan 2 = op N, plan 3 = op T/C): */
     BSM_TAB_CONTRIB = 8,      /* bsm_contrib records, grouped by output segment */
     BSM_TAB_SLICE = 9,        /* bsm_slice records (work items) */
     BSM_TAB_GATHER_ROWS = 10, /* int32: rows finalised by the gather pass (bit 31: already written) */
@@ -165,7 +166,8 @@ typedef enum {
     BSM_TAB_GATHER_POS = 12,  /* int64: positions in the partial-sum scratch */
     BSM_TAB_GROUP_PTR = 13,   /* int64: CSR over contributions per output segment ("block-row pointer";
                                  for plan 1 this is the transposed index) */
-    BSM_TAB_GROUP_SET = 14    /* int32: index-set id of every output segment */
+    BSM_TAB_GROUP_SET = 14,   /* int32: index-set id of every output segment */
+    BSM_TAB_CONTRIB_TOFF = 15 /* int64: scratch offset of the fused transposed partial of a contribution, -1 if none */
 } bsm_table;
 
 /* 32-byte device records (exported verbatim). */
@@ -173,8 +175,10 @@ typedef struct {
     int64_t off;       /* arena element offset of the block */
     int32_t m, n;      /* block is m x n, column-major, ld = m */
     int32_t in_set;    /* index set gathered from x */
-    int32_t form;      /* 0: y[out] += op(B) x[in] along block rows ("N-form");
-                          1: y[out] += op(B)^T x[in] along block columns ("T-form") */
+    int32_t form;      /* bit0 = 0: y[out] += op(B) x[in] along block rows ("N-form");
+                          bit0 = 1: y[out] += op(B)^T x[in] along block columns ("T-form");
+                          bit1: the same pass also emits t = op(B)^T x[out rows] to scratch (fused
+                          transposed partial of a half-stored symmetric block) */
     int32_t out_len;   /* outputs this block covers inside its segment (m or n) */
     int32_t block;     /* block id */
 } bsm_contrib;
@@ -183,7 +187,8 @@ typedef struct {
     int32_t out_set;     /* index set of the output segment */
     int32_t r0, r1;      /* output sub-range [r0, r1) of the segment handled by this work item */
     int32_t c_begin, c_end; /* contributions [c_begin, c_end) */
-    int32_t flags;       /* bit0: direct (writes y), else partial sums to scratch; bit1: vector loads ok */
+    int32_t flags;       /* bit0: direct (writes y), else partial sums to scratch; bit1: vector loads ok;
+                            bit2: whole segment, handled by the fused symmetric kernel */
     int64_t scratch_off; /* element offset of the partial vector when not direct */
 } bsm_slice;
 

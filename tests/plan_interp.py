@@ -40,12 +40,17 @@ class Sets:
         return self.pool[self.poff[s] + lo:self.poff[s] + hi].astype(np.int64)
 
 
-def run_plan(A, D, op, x, alpha=1.0, beta=0.0, beta_false=True, y=None, own=None):
+def run_plan(A, D, op, x, alpha=1.0, beta=0.0, beta_false=True, y=None, own=None, variant="auto"):
     plan = 0 if op == "N" else 1
+    fused_exists = D.table(L.TAB_SLICE, 2).size > 0
+    if variant == "fused" or (variant == "auto" and fused_exists):
+        assert fused_exists
+        plan += 2
     conj = op == "C"
     arena = build_arena(A, D)
     S = Sets(D)
     contrib = D.table(L.TAB_CONTRIB, plan)
+    toff = D.table(L.TAB_CONTRIB_TOFF, plan)
     slices = D.table(L.TAB_SLICE, plan)
     grow = D.table(L.TAB_GATHER_ROWS, plan)
     gptr = D.table(L.TAB_GATHER_PTR, plan)
@@ -54,19 +59,32 @@ def run_plan(A, D, op, x, alpha=1.0, beta=0.0, beta_false=True, y=None, own=None
     dt = np.result_type(D.dtype, x.dtype)
     y = np.zeros(nout, dt) if y is None else y
     nscratch = int(sum(int(s["r1"] - s["r0"]) for s in slices if not (s["flags"] & 1)))
+    nscratch += int(sum(int(c["n"]) for c in contrib if c["form"] & 2))
     scratch = np.full(nscratch, np.nan, dt)
+    seen_fused_first = True
+    for k in range(1, len(slices)):      # fused slices come first
+        assert not ((slices[k]["flags"] & 4) and not (slices[k - 1]["flags"] & 4))
     written = np.zeros(nout, np.int32)
     for s in slices:
         r0, r1 = int(s["r0"]), int(s["r1"])
         h = r1 - r0
-        assert 0 < h <= 128
+        fused = bool(s["flags"] & 4)
+        assert 0 < h <= (256 if fused else 128) and (r0 == 0 or not fused)
         acc = np.zeros(h, dt)
-        for c in contrib[s["c_begin"]:s["c_end"]]:
+        for ci in range(s["c_begin"], s["c_end"]):
+            c = contrib[ci]
             m, n = int(c["m"]), int(c["n"])
             B = arena[c["off"]:c["off"] + m * n].reshape((m, n), order="F")
             if conj:
                 B = B.conj()
-            if c["form"] == 0:
+            if c["form"] & 2:
+                assert fused and not (c["form"] & 1) and toff[ci] >= 0
+                t0 = int(toff[ci])
+                assert np.all(np.isnan(scratch[t0:t0 + n]))
+                scratch[t0:t0 + n] = B.T @ x[S.idx(s["out_set"], 0, m)]
+            else:
+                assert toff[ci] == -1
+            if (c["form"] & 1) == 0:
                 hi = min(r1, int(c["out_len"]))
                 if hi > r0:
                     acc[:hi - r0] += B[r0:hi, :] @ x[S.idx(c["in_set"], 0, n)]

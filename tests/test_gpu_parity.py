@@ -51,7 +51,11 @@ def golden(request):
 def test_symmetric_fixture(golden):
     A = B.SymmetricBlockMatrix(golden.diagonals, golden.diagonalindices, golden.offdiagonals,
                                golden.rowindices, golden.colindices, golden.size)
-    battery(A)
+    for variant in (L.VARIANT_FUSED, L.VARIANT_GATHER):
+        A.device().set_variant(variant)
+        battery(A)
+    A.device().set_variant(L.VARIANT_AUTO)
+    assert A.device().launch_count("N") == 2                     # fused kernel + finalize
     assert A.device().nnz() == B.nnz(A) == B.sparse(A).nnz      # test_symmetricblockmatrix.jl:99-107
     S = B.sparse(A)
     assert abs(S - S.T).nnz == 0                                 # issymmetric, :49
@@ -103,8 +107,18 @@ def test_c1_shape(dtype, permuted):
 
 
 @pytest.mark.parametrize("permuted", [False, True])
-def test_c2_shape(permuted):
-    A = G.symmetric_nearfield(seed=12, n=12000, k_near=4, permuted=permuted)
+@pytest.mark.parametrize("dtype", [np.complex128, np.float64, np.float32])
+def test_c2_shape(permuted, dtype):
+    A = G.symmetric_nearfield(seed=12, n=12000, k_near=4, permuted=permuted, dtype=dtype)
+    for variant in (L.VARIANT_FUSED, L.VARIANT_GATHER):
+        A.device().set_variant(variant)
+        battery(A, reps=1)
+
+
+def test_c2_tall_leaves_mix_fused_and_gather_kernels():
+    A = G.symmetric_nearfield(seed=19, n=20000, leaf_min=150, leaf_max=400, k_near=3)
+    sl = A.device().table(L.TAB_SLICE, 2)
+    assert 0 < ((sl["flags"] & 4) != 0).sum() < len(sl)
     battery(A, reps=1)
 
 

@@ -35,8 +35,14 @@ def test_sbm_plan(fixture, op):
     rng = np.random.default_rng(0)
     x = rng.standard_normal(A.size[1]) + 1j * rng.standard_normal(A.size[1])
     y0 = rng.standard_normal(A.size[0]) + 1j * rng.standard_normal(A.size[0])
-    assert rel(run_plan(P, D, op, x), O.mul_sbm(A, x, op)) < 1e-13
-    assert rel(run_plan(P, D, op, x, 1j, 2j, False, y0.copy()), O.mul_sbm(A, x, op, 1j, 2j, False, y0.copy())) < 1e-13
+    for variant in ("fused", "gather"):
+        assert rel(run_plan(P, D, op, x, variant=variant), O.mul_sbm(A, x, op)) < 1e-13
+        assert rel(run_plan(P, D, op, x, 1j, 2j, False, y0.copy(), variant=variant),
+                   O.mul_sbm(A, x, op, 1j, 2j, False, y0.copy())) < 1e-13
+    # fused plan: every half-stored block appears exactly once, no separate transposed segments
+    cf = D.table(L.TAB_CONTRIB, 2)
+    assert len(cf) == len(A.diagonals) + len(A.offdiagonals)
+    assert ((cf["form"] & 2) != 0).sum() == len(A.offdiagonals)
     # the leaf segments own their rows: diagonal + forward off-diagonal contributions are direct
     sl = D.table(L.TAB_SLICE, 0)
     assert (sl["flags"] & 1).sum() > 0
@@ -112,6 +118,32 @@ def test_overlapping_and_uncovered(dtype, contiguous):
         assert rel(run_plan(P, D, op, x, 0.5, -1.5, False, y0.copy()), ref5) < tol
 
 
+def test_symmetric_tall_leaves_mix_fused_and_gather():
+    # leaves taller than the fused kernel's 256 rows fall back to two separate contributions
+    rng = np.random.default_rng(10)
+    sizes = [300, 40, 257, 64, 256]
+    bounds = np.cumsum([0] + sizes)
+    idx = [np.arange(bounds[i] + 1, bounds[i + 1] + 1) for i in range(5)]
+    cplx = lambda m, n: rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))
+    diag = []
+    for sz in sizes:
+        d = cplx(sz, sz)
+        diag.append(np.asfortranarray(d + d.T))
+    off = [np.asfortranarray(cplx(sizes[i], sizes[i - 1] + sizes[0] * (i > 1))) for i in range(1, 5)]
+    rows = [idx[i] for i in range(1, 5)]
+    cols = [np.concatenate([idx[i - 1]] + ([idx[0]] if i > 1 else [])) for i in range(1, 5)]
+    n = int(bounds[-1])
+    A = O.OSBM(diag, idx, off, rows, cols, (n, n))
+    P = B.SymmetricBlockMatrix(diag, idx, off, rows, cols, (n, n))
+    D = host_only(P)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    for op in OPS:
+        for variant in ("fused", "gather"):
+            assert rel(run_plan(P, D, op, x, variant=variant), O.mul_sbm(A, x, op)) < 1e-13
+    sl = D.table(L.TAB_SLICE, 2)
+    assert 0 < (sl["flags"] & 4).astype(bool).sum() < len(sl)
+
+
 def test_tall_and_wide_blocks_are_sliced():
     rng = np.random.default_rng(4)
     blocks = [np.asfortranarray(rng.standard_normal((300, 7))), np.asfortranarray(rng.standard_normal((5, 700))),
@@ -178,6 +210,11 @@ def test_slab_plans_partition_the_product(fixture, op):
     for lo, hi in zip(cuts[:-1], cuts[1:]):
         D = host_only(P, own_rows=(lo, hi), own_cols=(lo, hi))
         run_plan(P, D, op, x, y=y, own=(lo, hi))
+    assert rel(y, ref) < 1e-13
+    y = np.zeros(n, np.complex128)
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        D = host_only(P, own_rows=(lo, hi), own_cols=(lo, hi))
+        run_plan(P, D, op, x, y=y, own=(lo, hi), variant="gather")
     assert rel(y, ref) < 1e-13
 
 
