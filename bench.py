@@ -349,8 +349,10 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = local_work["bytes"] / (k_ms * 1e-3) / 1e9
-    fused = spec["kind"] == "SymmetricBlockMatrix" and args.variant in (0, 2)
-    kernel_name = "sym_fused_kernel" if fused else "gather_gemv_kernel"
+    if spec["kind"] == "SymmetricBlockMatrix" and args.variant in (0, 2, 4):
+        kernel_name = "sym_fused_kernel" if args.variant == 2 else "sym_fused_tma_kernel"
+    else:
+        kernel_name = "gather_gemv_kernel"
     line = {
         "metric": METRIC, "value": work["bytes"] / (ms_step * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -358,7 +360,7 @@ def main():
         "gflops": work["flops"] / (ms_step * 1e-3) / 1e9,
         "config": {"workload": spec["desc"], "op": op, "l2": "working set larger than L2 (no flush needed)"
                    if work["bytes"] > 4 * 126e6 else "L2 flushed? no — working set fits L2, launch-bound case",
-                   "variant": {0: "auto", 1: "gather", 2: "fused", 3: "color"}[args.variant],
+                   "variant": {0: "auto", 1: "gather", 2: "fused", 3: "color", 4: "fused_tma"}[args.variant],
                    "parallelism": f"block-row slabs x{world}, NCCL all-gather of x" if world > 1 else "single GPU",
                    "algorithmic_bytes": work["bytes"], "flops": work["flops"],
                    "gen_s": round(t_gen, 1), "pack_s": round(t_pack, 1)},

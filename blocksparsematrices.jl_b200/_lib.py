@@ -13,7 +13,7 @@ LIB_PATH = Path(os.environ.get("BSM_B200_LIB", _HERE / "libbsm_b200.so"))
 F32, F64, C64 = 0, 1, 2
 OP_N, OP_T, OP_C = 0, 1, 2
 KIND_BLOCKSPARSE, KIND_SYMMETRIC, KIND_VBCRS = 0, 1, 2
-VARIANT_AUTO, VARIANT_GATHER, VARIANT_FUSED, VARIANT_COLOR = 0, 1, 2, 3
+VARIANT_AUTO, VARIANT_GATHER, VARIANT_FUSED, VARIANT_COLOR, VARIANT_FUSED_TMA = 0, 1, 2, 3, 4
 DEVICE_NONE = -2
 
 (TAB_ARENA, TAB_BLOCK_OFF, TAB_BLOCK_M, TAB_BLOCK_N, TAB_SET_LEN, TAB_SET_START, TAB_SET_POOL_OFF,

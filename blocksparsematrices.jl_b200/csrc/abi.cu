@@ -276,7 +276,8 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
 // GATHER plans are 0/1, FUSED plans 2/3 (symmetric matrices; AUTO picks FUSED when it exists).
 int plan_index(const bsm_matrix *A, int op) {
     const int base = (op == BSM_OP_N) ? 0 : 1;
-    const bool fused = A->H.has_fused && (A->variant == BSM_VARIANT_AUTO || A->variant == BSM_VARIANT_FUSED);
+    const bool fused = A->H.has_fused && (A->variant == BSM_VARIANT_AUTO || A->variant == BSM_VARIANT_FUSED ||
+                                          A->variant == BSM_VARIANT_FUSED_TMA);
     return base + (fused ? 2 : 0);
 }
 
@@ -288,12 +289,15 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
     const DevPlan &DP = A->plan[p];
     T *scratch = nullptr;
     const int32_t nfused = (int32_t)HP.n_fused_slices;
+    const bool use_tma = A->variant != BSM_VARIANT_FUSED;
     if (nfused > 0) {
         static bool attr_done[3] = {false, false, false};
         const int di = sizeof(T) == 4 ? 0 : sizeof(T) == 8 ? 1 : 2;
         if (!attr_done[di]) {
             CUDA_TRY(cudaFuncSetAttribute(sym_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)fused_smem_bytes<T>()));
+            CUDA_TRY(cudaFuncSetAttribute(sym_fused_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)fused_tma_smem_bytes<T>()));
             attr_done[di] = true;
         }
     }
@@ -324,7 +328,10 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
         const bool prof = A->profiling && nrhs == 1;
         if (prof) CUDA_TRY(cudaEventRecord(A->ev[0], st));
         if (nfused > 0) {
-            sym_fused_kernel<T><<<nfused, kFThreads, fused_smem_bytes<T>(), st>>>(a);
+            if (use_tma)
+                sym_fused_tma_kernel<T><<<nfused, kPThreads, fused_tma_smem_bytes<T>(), st>>>(a);
+            else
+                sym_fused_kernel<T><<<nfused, kFThreads, fused_smem_bytes<T>(), st>>>(a);
             CUDA_TRY(cudaGetLastError());
         }
         if (a.nslices > nfused) {
@@ -611,7 +618,7 @@ int bsm_destroy(bsm_handle h) {
 
 int bsm_set_variant(bsm_handle h, int variant) {
     if (int rc = check_handle(h)) return rc;
-    if (variant < BSM_VARIANT_AUTO || variant > BSM_VARIANT_COLOR) return fail(BSM_ERR_ARG, "bad variant");
+    if (variant < BSM_VARIANT_AUTO || variant > BSM_VARIANT_FUSED_TMA) return fail(BSM_ERR_ARG, "bad variant");
     h->variant = variant;
     return 0;
 }

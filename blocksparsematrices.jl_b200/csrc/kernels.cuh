@@ -412,6 +412,276 @@ constexpr size_t fused_smem_bytes() {
     return sizeof(T) * (size_t)(kXsCap + 2 * kFMaxRows + kFWarps * kFMaxRows);
 }
 
+// ---- fused symmetric kernel, TMA-staged -------------------------------------------------------------
+// Same work decomposition as sym_fused_kernel, but the block data never passes through registers on
+// its way from HBM: one producer thread streams whole-column chunks of every block with
+// cp.async.bulk (the TMA bulk-copy engine, SASS UBLKCP) into a ring of kPStages shared-memory stages;
+// completion is signalled on "full" mbarriers (complete_tx), 8 consumer warps compute from shared
+// memory and hand stages back through "empty" mbarriers. Loads in flight per SM = 2 CTAs x 4 stages x
+// 20 KB, independent of register pressure and occupancy.
+constexpr int kPStages = 4;
+constexpr int kPChunk = 20480;                 // payload bytes per stage
+constexpr int kPStageBytes = kPChunk + 128;    // + slack for the 16-byte alignment shift
+constexpr int kPThreads = kFThreads + 32;      // 8 consumer warps + 1 producer warp
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE_%=;\n"
+        "bra MBAR_WAIT_%=;\n"
+        "MBAR_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared bulk copy (16-byte aligned addresses, size multiple of 16), completes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar,
+                                         uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <class T>
+__device__ __forceinline__ int32_t chunk_cols(int32_t m) {
+    const int32_t cc = kPChunk / (m * (int32_t)sizeof(T));
+    return cc < 1 ? 1 : cc;
+}
+
+// One chunk (ncols whole columns of an m-row block) resident in shared memory.
+//   doN : accN[k] += op(B)[i_k, j] * xcol[j]
+//   doT : t[j] = sum_i op(B)[i, j] * xrow[i]  ->  tglobal[j] = t (fused partial, global scratch)
+//                                              or tsmem[j] += t (T-form contribution owned by the segment)
+template <class T, int RPL, bool CONJ>
+__device__ __forceinline__ void consume_chunk(const T *__restrict__ sm, int32_t m, int32_t ncols, int lane,
+                                              int warp, bool doN, bool doT, const T *__restrict__ xcol,
+                                              const T *__restrict__ xrow, T (&accN)[RPL], T *tglobal, T *tsmem) {
+    for (int32_t jc = 2 * warp; jc < ncols; jc += 2 * kFWarps) {
+        const bool hasB = (jc + 1) < ncols;
+        const T *cA = sm + jc * m;
+        const T *cB = cA + m;
+        const T xA = doN ? xcol[jc] : El<T>::zero();
+        const T xB = (doN && hasB) ? xcol[jc + 1] : El<T>::zero();
+        T tA = El<T>::zero(), tB = El<T>::zero();
+        // rows in groups of KG per lane: bounds the live registers of the 8-rows-per-lane case
+        constexpr int KG = RPL < 4 ? RPL : 4;
+#pragma unroll
+        for (int kg = 0; kg < RPL; kg += KG) {
+            T vA[KG], vB[KG];
+#pragma unroll
+            for (int k = 0; k < KG; ++k) {
+                const int32_t i = lane + 32 * (kg + k);
+                vA[k] = (i < m) ? cA[i] : El<T>::zero();
+                vB[k] = (hasB && i < m) ? cB[i] : El<T>::zero();
+                if (CONJ) {
+                    vA[k] = El<T>::conj(vA[k]);
+                    vB[k] = El<T>::conj(vB[k]);
+                }
+            }
+            if (doN) {
+#pragma unroll
+                for (int k = 0; k < KG; ++k) {
+                    El<T>::fma(accN[kg + k], vA[k], xA);
+                    El<T>::fma(accN[kg + k], vB[k], xB);
+                }
+            }
+            if (doT) {
+#pragma unroll
+                for (int k = 0; k < KG; ++k) {
+                    const T xr = xrow[lane + 32 * (kg + k)];
+                    El<T>::fma(tA, vA[k], xr);
+                    El<T>::fma(tB, vB[k], xr);
+                }
+            }
+        }
+        if (doT) {
+            const bool hi = (lane & 16) != 0;
+            const T send = hi ? tA : tB;
+            T v = El<T>::add(hi ? tB : tA, El<T>::shfl_xor(send, 16));
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) v = El<T>::add(v, El<T>::shfl_xor(v, o));
+            if (tglobal) {
+                if (lane == 0) tglobal[jc] = v;
+                if (lane == 16 && hasB) tglobal[jc + 1] = v;
+            } else {
+                if (lane == 0) tsmem[jc] = El<T>::add(tsmem[jc], v);
+                if (lane == 16 && hasB) tsmem[jc + 1] = El<T>::add(tsmem[jc + 1], v);
+            }
+        }
+    }
+}
+
+template <class T, int RPL, bool CONJ>
+__device__ __forceinline__ void tma_consumer(const MulArgs<T> &a, const bsm_slice &sl, unsigned char *stages,
+                                             T *xs, T *xrs, T *accT, uint64_t *full, uint64_t *empty) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;   // t < 256
+    const int32_t L = sl.r1;
+    const SetRef out = set_ref(a, sl.out_set);
+    // xrs is zero-padded to 256 rows and xs to the row count read below, so lanes past the block's
+    // height multiply by zero
+    xrs[t] = (t < L) ? a.x[out.at(t)] : El<T>::zero();
+    accT[t] = El<T>::zero();
+    T accN[RPL];
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) accN[k] = El<T>::zero();
+    uint32_t q = 0;
+    for (int32_t ci = sl.c_begin; ci < sl.c_end; ++ci) {
+        const bsm_contrib cb = a.contrib[ci];
+        const SetRef in = set_ref(a, cb.in_set);
+        const int32_t m = cb.m;
+        const int32_t cc = chunk_cols<T>(m);
+        const bool tform = (cb.form & 1) != 0;
+        const bool fusedT = (cb.form & 2) != 0;
+        T *tg = fusedT ? a.scratch + a.contrib_toff[ci] : nullptr;
+        if (tform) {
+            // x at the block's rows, once per contribution (m <= 256 <= kXsCap)
+            consumer_bar();
+            for (int32_t k = t; k < kFMaxRows; k += kFThreads) xs[k] = (k < m) ? a.x[in.at(k)] : El<T>::zero();
+            consumer_bar();
+        }
+        for (int32_t jw = 0; jw < cb.n; jw += kXsCap) {
+            const int32_t wend = min(cb.n, jw + kXsCap);
+            if (!tform) {
+                consumer_bar();
+                for (int32_t k = t; k < wend - jw; k += kFThreads) xs[k] = a.x[in.at(jw + k)];
+                consumer_bar();
+            }
+            for (int32_t j0 = jw; j0 < wend; j0 += cc, ++q) {
+                const int32_t ncols = min(cc, wend - j0);
+                const uint32_t stage = q % kPStages;
+                const uint32_t delta = (uint32_t)(((int64_t)j0 * m * (int64_t)sizeof(T)) & 15);
+                mbar_wait(&full[stage], (q / kPStages) & 1);
+                const T *sm = reinterpret_cast<const T *>(stages + stage * kPStageBytes + delta);
+                if (tform)
+                    consume_chunk<T, RPL, CONJ>(sm, m, ncols, lane, warp, false, true, nullptr, xs, accN, nullptr,
+                                                accT + j0);
+                else
+                    consume_chunk<T, RPL, CONJ>(sm, m, ncols, lane, warp, true, fusedT, xs + (j0 - jw), xrs, accN,
+                                                fusedT ? tg + j0 : nullptr, nullptr);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+            }
+        }
+    }
+    // every stage has been consumed: reuse the ring for the cross-warp reduction of the row sums
+    consumer_bar();
+    T *red = reinterpret_cast<T *>(stages);
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) red[warp * kFMaxRows + k * 32 + lane] = accN[k];
+    consumer_bar();
+    if (t < L) {
+        T tot = accT[t];
+#pragma unroll
+        for (int w = 0; w < kFWarps; ++w) tot = El<T>::add(tot, red[w * kFMaxRows + t]);
+        if (sl.flags & 1) {
+            const int32_t row = out.at(t);
+            T v = El<T>::mul(a.alpha, tot);
+            if (!a.beta_false) v = El<T>::add(v, El<T>::mul(a.beta, a.y[row]));
+            a.y[row] = v;
+        } else {
+            a.scratch[sl.scratch_off + t] = tot;
+        }
+    }
+}
+
+template <class T>
+__device__ __forceinline__ void tma_producer(const MulArgs<T> &a, const bsm_slice &sl, unsigned char *stages,
+                                             uint64_t *full, uint64_t *empty) {
+    const uint64_t policy = l2_evict_first_policy();
+    uint32_t q = 0;
+    for (int32_t ci = sl.c_begin; ci < sl.c_end; ++ci) {
+        const bsm_contrib cb = a.contrib[ci];
+        const int32_t m = cb.m;
+        const int32_t cc = chunk_cols<T>(m);
+        const unsigned char *blk = reinterpret_cast<const unsigned char *>(a.arena + cb.off);
+        for (int32_t jw = 0; jw < cb.n; jw += kXsCap) {
+            const int32_t wend = min(cb.n, jw + kXsCap);
+            for (int32_t j0 = jw; j0 < wend; j0 += cc, ++q) {
+                const int32_t ncols = min(cc, wend - j0);
+                const uint32_t stage = q % kPStages;
+                if (q >= kPStages) mbar_wait(&empty[stage], ((q / kPStages) - 1) & 1);
+                const int64_t boff = (int64_t)j0 * m * (int64_t)sizeof(T);
+                const uint32_t delta = (uint32_t)(boff & 15);
+                const uint32_t bytes = (delta + (uint32_t)ncols * (uint32_t)m * (uint32_t)sizeof(T) + 15u) & ~15u;
+                mbar_arrive_expect_tx(&full[stage], bytes);
+                bulk_g2s(stages + stage * kPStageBytes, blk + (boff - delta), bytes, &full[stage], policy);
+            }
+        }
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(kPThreads, 2) sym_fused_tma_kernel(const MulArgs<T> a) {
+    extern __shared__ __align__(128) unsigned char psm[];
+    unsigned char *stages = psm;                                        // kPStages * kPStageBytes
+    T *xs = reinterpret_cast<T *>(psm + kPStages * kPStageBytes);       // kXsCap
+    T *xrs = xs + kXsCap;                                               // kFMaxRows
+    T *accT = xrs + kFMaxRows;                                          // kFMaxRows
+    uint64_t *full = reinterpret_cast<uint64_t *>(accT + kFMaxRows);    // kPStages
+    uint64_t *empty = full + kPStages;                                  // kPStages
+    const bsm_slice sl = a.slices[blockIdx.x];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kPStages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kFWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x >= kFThreads) {
+        if (threadIdx.x == kFThreads) tma_producer<T>(a, sl, stages, full, empty);
+        return;
+    }
+    const int32_t L = sl.r1;
+    if (a.conj) {
+        if (L <= 64)
+            tma_consumer<T, 2, true>(a, sl, stages, xs, xrs, accT, full, empty);
+        else if (L <= 128)
+            tma_consumer<T, 4, true>(a, sl, stages, xs, xrs, accT, full, empty);
+        else
+            tma_consumer<T, 8, true>(a, sl, stages, xs, xrs, accT, full, empty);
+    } else {
+        if (L <= 64)
+            tma_consumer<T, 2, false>(a, sl, stages, xs, xrs, accT, full, empty);
+        else if (L <= 128)
+            tma_consumer<T, 4, false>(a, sl, stages, xs, xrs, accT, full, empty);
+        else
+            tma_consumer<T, 8, false>(a, sl, stages, xs, xrs, accT, full, empty);
+    }
+}
+
+template <class T>
+constexpr size_t fused_tma_smem_bytes() {
+    return (size_t)kPStages * kPStageBytes + sizeof(T) * (size_t)(kXsCap + 2 * kFMaxRows) + 2 * kPStages * 8;
+}
+static_assert(kPStages * kPStageBytes >= kFWarps * kFMaxRows * 16, "reduction buffer must fit in the ring");
+
 template <class T>
 struct FinalizeArgs {
     const int32_t *rows;

@@ -147,7 +147,7 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
             if (ci.out_len > S.len[gset[g]]) return "contribution longer than its output segment";
             if (S.len[ci.in_set] < (ci.form == 0 ? b.n : b.m)) return "input set shorter than block";
             P.contrib.push_back(d);
-            P.applied_entries += (int64_t)b.m * b.n;
+            P.applied_entries += (int64_t)b.m * b.n * (ci.fuse_tset >= 0 ? 2 : 1);
         }
     }
 

@@ -62,7 +62,9 @@ typedef enum {
                                 half-stored symmetric blocks) */
     BSM_VARIANT_FUSED = 2,   /* symmetric: one pass over each half-stored block, transposed partials
                                 gathered through the transposed index */
-    BSM_VARIANT_COLOR = 3    /* colour-ordered multi-launch (the reference's schedule, for comparison) */
+    BSM_VARIANT_COLOR = 3,   /* colour-ordered multi-launch (the reference's schedule, for comparison) */
+    BSM_VARIANT_FUSED_TMA = 4 /* FUSED with the blocks streamed by cp.async.bulk (TMA) into an mbarrier
+                                ring of shared-memory stages; what AUTO picks for symmetric matrices */
 } bsm_variant;
 
 /* Creation options; pass NULL for defaults. */

@@ -51,7 +51,7 @@ def golden(request):
 def test_symmetric_fixture(golden):
     A = B.SymmetricBlockMatrix(golden.diagonals, golden.diagonalindices, golden.offdiagonals,
                                golden.rowindices, golden.colindices, golden.size)
-    for variant in (L.VARIANT_FUSED, L.VARIANT_GATHER):
+    for variant in (L.VARIANT_FUSED_TMA, L.VARIANT_FUSED, L.VARIANT_GATHER):
         A.device().set_variant(variant)
         battery(A)
     A.device().set_variant(L.VARIANT_AUTO)
@@ -110,7 +110,7 @@ def test_c1_shape(dtype, permuted):
 @pytest.mark.parametrize("dtype", [np.complex128, np.float64, np.float32])
 def test_c2_shape(permuted, dtype):
     A = G.symmetric_nearfield(seed=12, n=12000, k_near=4, permuted=permuted, dtype=dtype)
-    for variant in (L.VARIANT_FUSED, L.VARIANT_GATHER):
+    for variant in (L.VARIANT_FUSED_TMA, L.VARIANT_FUSED, L.VARIANT_GATHER):
         A.device().set_variant(variant)
         battery(A, reps=1)
 
