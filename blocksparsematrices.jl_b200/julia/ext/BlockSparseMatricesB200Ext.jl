@@ -1,0 +1,125 @@
+# BlockSparseMatricesB200Ext.jl — package extension that binds libbsm_b200.so (include/bsm_b200.h)
+# behind BlockSparseMatrices.jl's own operator API. Modelled on ext/BlockUnicodePlots of the reference
+# (Project.toml [weakdeps]/[extensions]); triggered by loading the tiny carrier package `BSMB200`
+# (which only locates the shared library, see INTEGRATION.md).
+#
+# NOT RUN IN THIS REPOSITORY'S CI: the build image has no Julia. The file is kept thin on purpose —
+# marshalling only; every numerical statement is tested through the same C ABI from tests/ (ctypes).
+#
+# No CUDA.jl kernels, no CPU fallback: a B200Matrix multiplies only through ccall.
+module BlockSparseMatricesB200Ext
+
+using BlockSparseMatrices
+using BlockSparseMatrices: AbstractBlockMatrix, BlockSparseMatrix, SymmetricBlockMatrix,
+                           VariableBlockCompressedRowStorage
+using LinearAlgebra, LinearMaps, SparseArrays
+import BSMB200: libbsm_b200          # const libbsm_b200 = "/path/to/libbsm_b200.so"
+
+const BSM_DTYPE = Dict(Float32 => Cint(0), Float64 => Cint(1), ComplexF64 => Cint(2))
+const OP_N, OP_T, OP_C = Cint(0), Cint(1), Cint(2)
+
+struct BsmOptions                     # mirrors bsm_options
+    device::Int32
+    variant::Int32
+    own_row_lo::Int64
+    own_row_hi::Int64
+    own_col_lo::Int64
+    own_col_hi::Int64
+    reserved::NTuple{4,Int64}
+end
+BsmOptions(; device=-1, variant=0) = BsmOptions(device, variant, 0, -1, 0, -1, (0, 0, 0, 0))
+
+check(rc) = rc == 0 || error("libbsm_b200: " * unsafe_string(ccall((:bsm_last_error, libbsm_b200), Cstring, ())))
+
+"""
+    B200Matrix(A)   # A::BlockSparseMatrix | SymmetricBlockMatrix | VariableBlockCompressedRowStorage
+
+Device-resident copy of `A` (arena + index tables in HBM). `<: AbstractBlockMatrix{T}`, so `*`, `mul!`,
+`adjoint`, `transpose`, `A[:, :]` and Krylov solvers work through LinearMaps unchanged.
+"""
+mutable struct B200Matrix{T} <: AbstractBlockMatrix{T}
+    handle::Ptr{Cvoid}
+    size::Tuple{Int,Int}
+    function B200Matrix{T}(h, sz) where {T}
+        A = new{T}(h, sz)
+        finalizer(a -> ccall((:bsm_destroy, libbsm_b200), Cint, (Ptr{Cvoid},), a.handle), A)
+        return A
+    end
+end
+
+pool(vs) = (reduce(vcat, vs; init=Int64[]), Int64[0; cumsum(length.(vs))])
+colmajor(T, b) = b isa Matrix{T} ? b : Matrix{T}(b)     # materialises lazy wrappers
+
+function B200Matrix(A::BlockSparseMatrix{T}; kw...) where {T}
+    blocks = [colmajor(T, b) for b in A.blocks]
+    ptrs = Ptr{Cvoid}[pointer(b) for b in blocks]
+    m, n = Int64.(size.(blocks, 1)), Int64.(size.(blocks, 2))
+    ri, rp = pool(A.rowindices); ci, cp = pool(A.colindices)
+    h = Ref{Ptr{Cvoid}}(C_NULL); opt = Ref(BsmOptions(; kw...))
+    GC.@preserve blocks check(ccall((:bsm_create_blocksparse, libbsm_b200), Cint,
+        (Cint, Int64, Int64, Int64, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64},
+         Ptr{Int64}, Ptr{Int64}, Ref{BsmOptions}, Ref{Ptr{Cvoid}}),
+        BSM_DTYPE[T], A.size[1], A.size[2], length(blocks), ptrs, m, n, ri, rp, ci, cp, opt, h))
+    return B200Matrix{T}(h[], A.size)
+end
+
+function B200Matrix(A::SymmetricBlockMatrix{T}; kw...) where {T}
+    D = [colmajor(T, b) for b in A.diagonals]; O = [colmajor(T, b) for b in A.offdiagonals]
+    dp = Ptr{Cvoid}[pointer(b) for b in D]; op = Ptr{Cvoid}[pointer(b) for b in O]
+    di, dptr = pool(A.diagonalindices); ri, rp = pool(A.rowindices); ci, cp = pool(A.colindices)
+    h = Ref{Ptr{Cvoid}}(C_NULL); opt = Ref(BsmOptions(; kw...))
+    GC.@preserve D O check(ccall((:bsm_create_symmetric, libbsm_b200), Cint,
+        (Cint, Int64, Int64, Int64, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int64,
+         Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64},
+         Ref{BsmOptions}, Ref{Ptr{Cvoid}}),
+        BSM_DTYPE[T], A.size[1], A.size[2], length(D), dp, Int64.(size.(D, 1)), di, dptr, length(O), op,
+        Int64.(size.(O, 1)), Int64.(size.(O, 2)), ri, rp, ci, cp, opt, h))
+    return B200Matrix{T}(h[], A.size)
+end
+
+function B200Matrix(A::VariableBlockCompressedRowStorage{T}; kw...) where {T}
+    # blocks may be lazy `transpose(parent)` wrappers (SymmetricBlockMatrix → VBCRS conversion,
+    # src/vbcrs.jl:222-264): hand the parent over and let the packer materialise the transpose
+    istr = UInt8[b isa Transpose ? 1 : 0 for b in A.blocks]
+    keep = [b isa Transpose ? colmajor(T, parent(b)) : colmajor(T, b) for b in A.blocks]
+    ptrs = Ptr{Cvoid}[pointer(b) for b in keep]
+    m, n = Int64.(size.(A.blocks, 1)), Int64.(size.(A.blocks, 2))
+    h = Ref{Ptr{Cvoid}}(C_NULL); opt = Ref(BsmOptions(; kw...))
+    GC.@preserve keep check(ccall((:bsm_create_vbcrs, libbsm_b200), Cint,
+        (Cint, Int64, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Int64},
+         Ptr{Int64}, Ptr{UInt8}, Ref{BsmOptions}, Ref{Ptr{Cvoid}}),
+        BSM_DTYPE[T], A.size[1], A.size[2], length(A.rowptr) - 1, length(keep), Int64.(A.rowptr),
+        Int64.(A.colindices), Int64.(A.rowindices), ptrs, m, n, istr, opt, h))
+    return B200Matrix{T}(h[], A.size)
+end
+
+SparseArrays.nnz(A::B200Matrix) = Int(ccall((:bsm_nnz, libbsm_b200), Int64, (Ptr{Cvoid},), A.handle))
+SparseArrays.nnz(A::Union{LinearMaps.AdjointMap{<:Any,<:B200Matrix},LinearMaps.TransposeMap{<:Any,<:B200Matrix}}) = nnz(A.lmap)
+
+opcode(::B200Matrix) = OP_N
+opcode(::LinearMaps.TransposeMap{<:Any,<:B200Matrix}) = OP_T
+opcode(::LinearMaps.AdjointMap{<:Any,<:B200Matrix}) = OP_C
+parentmap(A::B200Matrix) = A
+parentmap(A) = A.lmap
+
+const B200Map{T} = Union{B200Matrix{T},LinearMaps.AdjointMap{T,<:B200Matrix{T}},LinearMaps.TransposeMap{T,<:B200Matrix{T}}}
+
+# host Arrays: bsm_mul_host copies x in and y out. β === false is Julia's strong zero
+# (src/abstractblockmatrix.jl:33) and is passed as beta_is_false = 1.
+function LinearMaps._unsafe_mul!(y::StridedVecOrMat{T}, A::B200Map{T}, x::StridedVecOrMat{T},
+                                 α::Number=true, β::Number=false) where {T}
+    P = parentmap(A)
+    a, b = Ref(T(α)), Ref(T(β))
+    check(ccall((:bsm_mul_host, libbsm_b200), Cint,
+        (Ptr{Cvoid}, Cint, Ref{T}, Ref{T}, Cint, Ptr{T}, Int64, Ptr{T}, Int64, Int64),
+        P.handle, opcode(A), a, b, β === false, x, stride(x, 2), y, stride(y, 2), size(x, 2)))
+    return y
+end
+
+# mixed element types (ComplexF64 blocks × Float64 x, as in test/test_vbcrs.jl:34-35): promote x
+function LinearMaps._unsafe_mul!(y::AbstractVecOrMat{T}, A::B200Map{T}, x::AbstractVecOrMat, α::Number=true,
+                                 β::Number=false) where {T}
+    return LinearMaps._unsafe_mul!(y, A, convert(Array{T}, x), α, β)
+end
+
+end # module
