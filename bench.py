@@ -349,10 +349,10 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = local_work["bytes"] / (k_ms * 1e-3) / 1e9
-    if spec["kind"] == "SymmetricBlockMatrix" and args.variant in (0, 2, 4):
-        kernel_name = "sym_fused_kernel" if args.variant == 2 else "sym_fused_tma_kernel"
-    else:
-        kernel_name = "gather_gemv_kernel"
+    stats = D.plan_stats(op)
+    kernel_name = max(stats["bytes"], key=stats["bytes"].get)
+    if kernel_name == "sym_fused_tma_kernel" and args.variant == 2:
+        kernel_name = "sym_fused_kernel"
     line = {
         "metric": METRIC, "value": work["bytes"] / (ms_step * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -363,7 +363,7 @@ def main():
                    "variant": {0: "auto", 1: "gather", 2: "fused", 3: "color", 4: "fused_tma"}[args.variant],
                    "parallelism": f"block-row slabs x{world}, NCCL all-gather of x" if world > 1 else "single GPU",
                    "algorithmic_bytes": work["bytes"], "flops": work["flops"],
-                   "gen_s": round(t_gen, 1), "pack_s": round(t_pack, 1)},
+                   "gen_s": round(t_gen, 1), "pack_s": round(t_pack, 1), "plan": stats},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": kernel_name, "kernel_ms": k_ms,
                      "finalize_ms": float(np.mean(fin_ms)), "peak_source": peak_src,

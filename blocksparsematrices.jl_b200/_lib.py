@@ -18,7 +18,7 @@ DEVICE_NONE = -2
 
 (TAB_ARENA, TAB_BLOCK_OFF, TAB_BLOCK_M, TAB_BLOCK_N, TAB_SET_LEN, TAB_SET_START, TAB_SET_POOL_OFF,
  TAB_POOL, TAB_CONTRIB, TAB_SLICE, TAB_GATHER_ROWS, TAB_GATHER_PTR, TAB_GATHER_POS, TAB_GROUP_PTR,
- TAB_GROUP_SET, TAB_CONTRIB_TOFF) = range(16)
+ TAB_GROUP_SET, TAB_CONTRIB_TOFF, TAB_WCHUNK, TAB_WITEM_PTR) = range(18)
 
 
 class Options(ctypes.Structure):
@@ -62,6 +62,7 @@ SIGNATURES = [
     ("bsm_work", c_int, [c_void_p, c_int, c_int64, c_int, POINTER(c_double), POINTER(c_double),
                          POINTER(c_double)]),
     ("bsm_launch_count", c_int, [c_void_p, c_int]),
+    ("bsm_plan_stats", c_int, [c_void_p, c_int, _P64]),
     ("bsm_table_count", c_int64, [c_void_p, c_int, c_int]),
     ("bsm_table_copy", c_int, [c_void_p, c_int, c_int, c_void_p, c_int64]),
     ("bsm_device_count", c_int, [POINTER(c_int)]),

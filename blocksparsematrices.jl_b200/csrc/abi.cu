@@ -59,7 +59,11 @@ struct DevPlan {
     DevBuf<bsm_slice> slices;
     DevBuf<int32_t> gather_rows;
     DevBuf<int64_t> gather_ptr, gather_pos;
+    DevBuf<bsm_wchunk> wchunk;
+    DevBuf<int32_t> witem_ptr;
     void release() {
+        wchunk.release();
+        witem_ptr.release();
         contrib.release();
         contrib_toff.release();
         slices.release();
@@ -209,6 +213,8 @@ int upload_tables(bsm_matrix *A) {
         if (int rc = A->plan[p].gather_rows.upload(H.plan[p].gather_rows)) return rc;
         if (int rc = A->plan[p].gather_ptr.upload(H.plan[p].gather_ptr)) return rc;
         if (int rc = A->plan[p].gather_pos.upload(H.plan[p].gather_pos)) return rc;
+        if (int rc = A->plan[p].wchunk.upload(H.plan[p].wchunk)) return rc;
+        if (int rc = A->plan[p].witem_ptr.upload(H.plan[p].witem_ptr)) return rc;
     }
     return 0;
 }
@@ -235,6 +241,7 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
     if (err.empty()) err = build_plan(H, ir[1], H.ncols, H.nrows, pp[1], H.plan[1]);
     if (H.has_fused) {
         pp[0].fused = pp[1].fused = true;
+        pp[0].warp_stream = pp[1].warp_stream = H.kind != BSM_KIND_SYMMETRIC;
         if (err.empty()) err = build_plan(H, ir[2], H.nrows, H.ncols, pp[0], H.plan[2]);
         if (err.empty()) err = build_plan(H, ir[3], H.ncols, H.nrows, pp[1], H.plan[3]);
     }
@@ -289,15 +296,20 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
     const DevPlan &DP = A->plan[p];
     T *scratch = nullptr;
     const int32_t nfused = (int32_t)HP.n_fused_slices;
+    const int32_t nwarp = (int32_t)HP.n_warp_slices;
     const bool use_tma = A->variant != BSM_VARIANT_FUSED;
-    if (nfused > 0) {
+    if (nfused > 0 || nwarp > 0) {
         static bool attr_done[3] = {false, false, false};
         const int di = sizeof(T) == 4 ? 0 : sizeof(T) == 8 ? 1 : 2;
         if (!attr_done[di]) {
             CUDA_TRY(cudaFuncSetAttribute(sym_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)fused_smem_bytes<T>()));
-            CUDA_TRY(cudaFuncSetAttribute(sym_fused_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            CUDA_TRY(cudaFuncSetAttribute(sym_fused_tma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)fused_tma_smem_bytes<T>()));
+            CUDA_TRY(cudaFuncSetAttribute(sym_fused_tma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)fused_tma_smem_bytes<T>()));
+            CUDA_TRY(cudaFuncSetAttribute(stream_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)stream_warp_smem_bytes<T>()));
             attr_done[di] = true;
         }
     }
@@ -329,15 +341,36 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
         if (prof) CUDA_TRY(cudaEventRecord(A->ev[0], st));
         if (nfused > 0) {
             if (use_tma)
-                sym_fused_tma_kernel<T><<<nfused, kPThreads, fused_tma_smem_bytes<T>(), st>>>(a);
+                if (HP.fused_general)
+                    sym_fused_tma_kernel<T, true><<<nfused, kPThreads, fused_tma_smem_bytes<T>(), st>>>(a);
+                else
+                    sym_fused_tma_kernel<T, false><<<nfused, kPThreads, fused_tma_smem_bytes<T>(), st>>>(a);
             else
                 sym_fused_kernel<T><<<nfused, kFThreads, fused_smem_bytes<T>(), st>>>(a);
             CUDA_TRY(cudaGetLastError());
         }
-        if (a.nslices > nfused) {
+        if (nwarp > 0) {
+            WarpArgs<T> w;
+            w.arena = (const unsigned char *)A->arena;
+            w.chunks = DP.wchunk.p;
+            w.item_ptr = DP.witem_ptr.p;
+            w.pool = A->pool.p;
+            w.x = a.x;
+            w.y = a.y;
+            w.scratch = scratch;
+            w.alpha = a.alpha;
+            w.beta = a.beta;
+            w.nitems = (int32_t)HP.witem_ptr.size() - 1;
+            w.beta_false = a.beta_false;
+            w.conj = a.conj;
+            stream_warp_kernel<T><<<(unsigned)((w.nitems + kWWarps - 1) / kWWarps), kWWarps * 32,
+                                    stream_warp_smem_bytes<T>(), st>>>(w);
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (a.nslices > nfused + nwarp) {
             MulArgs<T> b = a;
-            b.slices = a.slices + nfused;
-            b.nslices = a.nslices - nfused;
+            b.slices = a.slices + nfused + nwarp;
+            b.nslices = a.nslices - nfused - nwarp;
             gather_gemv_kernel<T, VMAX><<<b.nslices, kThreads, 0, st>>>(b);
             CUDA_TRY(cudaGetLastError());
         }
@@ -408,7 +441,8 @@ int bsm_create_blocksparse(int dtype, int64_t nrows, int64_t ncols, int64_t nb,
     H.kind = BSM_KIND_BLOCKSPARSE;
     H.nrows = nrows;
     H.ncols = ncols;
-    std::vector<ContribIR> ir[2];
+    H.has_fused = true;
+    std::vector<ContribIR> ir[4];
     for (int64_t b = 0; b < nb; ++b) {
         if (m[b] < 0 || n[b] < 0 || rowptr[b + 1] - rowptr[b] != m[b] || colptr[b + 1] - colptr[b] != n[b] ||
             (m[b] * n[b] > 0 && !blocks[b])) {
@@ -428,6 +462,8 @@ int bsm_create_blocksparse(int dtype, int64_t nrows, int64_t ncols, int64_t nb,
         // wrappers swap the index vectors (/root/reference/src/symmetricblockmatrix.jl:345-365)
         ir[1].push_back(ContribIR{(int32_t)b, 1, cs, rs, (int32_t)n[b]});
     }
+    ir[2] = ir[0];  // stream plans: same contributions, TMA-staged kernels
+    ir[3] = ir[1];
     return finish_create(A, ir, opt, out);
 }
 
@@ -577,7 +613,8 @@ int bsm_create_vbcrs(int dtype, int64_t nrows, int64_t ncols, int64_t nbrows, in
         else
             it->second = std::max(it->second, rowlen[r]);
     }
-    std::vector<ContribIR> ir[2];
+    H.has_fused = true;
+    std::vector<ContribIR> ir[4];
     for (int64_t b = 0; b < nb; ++b) {
         const int64_t r = brow_of[b];
         const bool tr = is_transposed && is_transposed[b];
@@ -590,6 +627,8 @@ int bsm_create_vbcrs(int dtype, int64_t nrows, int64_t ncols, int64_t nbrows, in
         ir[0].push_back(ContribIR{(int32_t)b, 0, out_rows, in_cols, (int32_t)m[b]});   // src/vbcrs.jl:277-284
         ir[1].push_back(ContribIR{(int32_t)b, 1, out_cols, in_rows, (int32_t)n[b]});   // src/vbcrs.jl:315-326
     }
+    ir[2] = ir[0];  // stream plans: same contributions, TMA-staged kernels
+    ir[3] = ir[1];
     return finish_create(A, ir, opt, out);
 }
 
@@ -605,8 +644,7 @@ int bsm_destroy(bsm_handle h) {
     h->set_start.release();
     h->set_pool_off.release();
     h->pool.release();
-    h->plan[0].release();
-    h->plan[1].release();
+    for (int p = 0; p < 4; ++p) h->plan[p].release();
     if (h->hx) cudaFree(h->hx);
     if (h->hy) cudaFree(h->hy);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
@@ -738,6 +776,7 @@ int bsm_work(bsm_handle h, int op, int64_t nrhs, int beta_used, double *bytes, d
     const HostPlan &P = H.plan[plan_index(h, op)];
     const double s = dtype_size(H.dtype);
     const double tab = (double)P.contrib.size() * sizeof(bsm_contrib) + (double)P.slices.size() * sizeof(bsm_slice) +
+                       (double)P.wchunk.size() * sizeof(bsm_wchunk) +
                        (double)H.sets.pool.size() * 4 + (double)H.sets.len.size() * 16 +
                        (double)P.gather_rows.size() * 12 + (double)P.gather_pos.size() * 8;
     if (bytes)
@@ -747,11 +786,34 @@ int bsm_work(bsm_handle h, int op, int64_t nrhs, int beta_used, double *bytes, d
     return 0;
 }
 
+int bsm_plan_stats(bsm_handle h, int op, int64_t out[10]) {
+    if (int rc = check_handle(h)) return rc;
+    if (op < BSM_OP_N || op > BSM_OP_C || !out) return fail(BSM_ERR_ARG, "bad op or null output");
+    const HostPlan &P = h->H.plan[plan_index(h, op)];
+    const int64_t s = dtype_size(h->H.dtype);
+    for (int i = 0; i < 10; ++i) out[i] = 0;
+    for (size_t i = 0; i < P.slices.size(); ++i) {
+        const bsm_slice &sl = P.slices[i];
+        const int cls = (sl.flags & kSliceFused) ? 0 : (sl.flags & kSliceWarp) ? 1 : 2;
+        out[cls]++;
+        for (int32_t c = sl.c_begin; c < sl.c_end; ++c) {
+            const bsm_contrib &cb = P.contrib[c];
+            const int64_t lo = sl.r0, hi = std::min<int64_t>(sl.r1, cb.out_len);
+            if (hi > lo) out[3 + cls] += (hi - lo) * ((cb.form & kFormT) ? cb.m : cb.n) * s;
+        }
+    }
+    out[6] = P.witem_ptr.empty() ? 0 : (int64_t)P.witem_ptr.size() - 1;
+    out[7] = (int64_t)P.wchunk.size();
+    out[8] = P.scratch_elems;
+    out[9] = (int64_t)P.gather_rows.size();
+    return 0;
+}
+
 int bsm_launch_count(bsm_handle h, int op) {
     if (!h || op < BSM_OP_N || op > BSM_OP_C) return BSM_ERR_ARG;
     const HostPlan &P = h->H.plan[plan_index(h, op)];
-    return (P.n_fused_slices > 0 ? 1 : 0) + ((int64_t)P.slices.size() > P.n_fused_slices ? 1 : 0) +
-           (P.gather_rows.empty() ? 0 : 1);
+    return (P.n_fused_slices > 0 ? 1 : 0) + (P.n_warp_slices > 0 ? 1 : 0) +
+           ((int64_t)P.slices.size() > P.n_fused_slices + P.n_warp_slices ? 1 : 0) + (P.gather_rows.empty() ? 0 : 1);
 }
 
 }  // extern "C"
@@ -804,6 +866,8 @@ TabView table_view(bsm_handle h, int table, int plan, std::vector<int32_t> &tmp3
     case BSM_TAB_GROUP_PTR: return view(P.group_ptr);
     case BSM_TAB_GROUP_SET: return view(P.group_set);
     case BSM_TAB_CONTRIB_TOFF: return view(P.contrib_toff);
+    case BSM_TAB_WCHUNK: return view(P.wchunk);
+    case BSM_TAB_WITEM_PTR: return view(P.witem_ptr);
     }
     return t;
 }

@@ -537,15 +537,49 @@ __device__ __forceinline__ void consume_chunk(const T *__restrict__ sm, int32_t 
     }
 }
 
-template <class T, int RPL, bool CONJ>
+// T-form chunk of a block of any height (m <= kXsCap): one warp per column, lanes stride over the rows,
+// shuffle reduction. Columns are dealt to the warps by their ABSOLUTE index (j % 8), so that with only a
+// few tall columns per stage the eight warps still work concurrently, each on a different stage.
+template <class T, bool CONJ>
+__device__ __forceinline__ void consume_chunk_tall(const T *__restrict__ sm, int32_t m, int32_t ncols,
+                                                   int32_t jabs0, int lane, int warp,
+                                                   const T *__restrict__ xrow, T *tsmem) {
+    for (int32_t jc = (warp - jabs0) & (kFWarps - 1); jc < ncols; jc += kFWarps) {
+        const T *col = sm + jc * m;
+        T s0 = El<T>::zero(), s1 = El<T>::zero(), s2 = El<T>::zero(), s3 = El<T>::zero();
+        int32_t i = lane;
+        for (; i + 96 < m; i += 128) {
+            const T v0 = col[i], v1 = col[i + 32], v2 = col[i + 64], v3 = col[i + 96];
+            El<T>::fma(s0, CONJ ? El<T>::conj(v0) : v0, xrow[i]);
+            El<T>::fma(s1, CONJ ? El<T>::conj(v1) : v1, xrow[i + 32]);
+            El<T>::fma(s2, CONJ ? El<T>::conj(v2) : v2, xrow[i + 64]);
+            El<T>::fma(s3, CONJ ? El<T>::conj(v3) : v3, xrow[i + 96]);
+        }
+        for (; i < m; i += 32) {
+            const T v0 = col[i];
+            El<T>::fma(s0, CONJ ? El<T>::conj(v0) : v0, xrow[i]);
+        }
+        T v = El<T>::add(El<T>::add(s0, s1), El<T>::add(s2, s3));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = El<T>::add(v, El<T>::shfl_xor(v, o));
+        if (lane == 0) tsmem[jc] = El<T>::add(tsmem[jc], v);
+    }
+}
+
+// GEN = false: whole segments whose T-form blocks are no taller than the rows the lanes hold (every
+// SymmetricBlockMatrix plan); GEN = true adds column sub-ranges of long all-T-form segments and T-form
+// blocks of up to kXsCap rows (consume_chunk_tall). Two instantiations, because the extra paths cost the
+// lean one registers (and 7 % of its bandwidth on C2).
+template <class T, int RPL, bool CONJ, bool GEN>
 __device__ __forceinline__ void tma_consumer(const MulArgs<T> &a, const bsm_slice &sl, unsigned char *stages,
                                              T *xs, T *xrs, T *accT, uint64_t *full, uint64_t *empty) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;   // t < 256
-    const int32_t L = sl.r1;
+    const int32_t r0 = GEN ? sl.r0 : 0;   // > 0 only for column sub-ranges of all-T-form segments
+    const int32_t L = sl.r1 - r0;
     const SetRef out = set_ref(a, sl.out_set);
     // xrs is zero-padded to 256 rows and xs to the row count read below, so lanes past the block's
     // height multiply by zero
-    xrs[t] = (t < L) ? a.x[out.at(t)] : El<T>::zero();
+    xrs[t] = (r0 == 0 && t < L) ? a.x[out.at(t)] : El<T>::zero();
     accT[t] = El<T>::zero();
     T accN[RPL];
 #pragma unroll
@@ -558,15 +592,20 @@ __device__ __forceinline__ void tma_consumer(const MulArgs<T> &a, const bsm_slic
         const int32_t cc = chunk_cols<T>(m);
         const bool tform = (cb.form & 1) != 0;
         const bool fusedT = (cb.form & 2) != 0;
+        const int32_t jlo = tform ? r0 : 0;
+        const int32_t jhi = tform ? min(sl.r1, cb.out_len) : cb.n;
+        if (jhi <= jlo || m == 0) continue;
+        const bool tall = GEN && tform && m > 32 * RPL;
         T *tg = fusedT ? a.scratch + a.contrib_toff[ci] : nullptr;
         if (tform) {
-            // x at the block's rows, once per contribution (m <= 256 <= kXsCap)
+            // x at the block's rows, once per contribution (m <= kXsCap)
+            const int32_t mpad = GEN ? max(m, kFMaxRows) : kFMaxRows;
             consumer_bar();
-            for (int32_t k = t; k < kFMaxRows; k += kFThreads) xs[k] = (k < m) ? a.x[in.at(k)] : El<T>::zero();
+            for (int32_t k = t; k < mpad; k += kFThreads) xs[k] = (k < m) ? a.x[in.at(k)] : El<T>::zero();
             consumer_bar();
         }
-        for (int32_t jw = 0; jw < cb.n; jw += kXsCap) {
-            const int32_t wend = min(cb.n, jw + kXsCap);
+        for (int32_t jw = jlo; jw < jhi; jw += kXsCap) {
+            const int32_t wend = min(jhi, jw + kXsCap);
             if (!tform) {
                 consumer_bar();
                 for (int32_t k = t; k < wend - jw; k += kFThreads) xs[k] = a.x[in.at(jw + k)];
@@ -578,9 +617,11 @@ __device__ __forceinline__ void tma_consumer(const MulArgs<T> &a, const bsm_slic
                 const uint32_t delta = (uint32_t)(((int64_t)j0 * m * (int64_t)sizeof(T)) & 15);
                 mbar_wait(&full[stage], (q / kPStages) & 1);
                 const T *sm = reinterpret_cast<const T *>(stages + stage * kPStageBytes + delta);
-                if (tform)
+                if (GEN && tall)
+                    consume_chunk_tall<T, CONJ>(sm, m, ncols, j0, lane, warp, xs, accT + (j0 - r0));
+                else if (tform)
                     consume_chunk<T, RPL, CONJ>(sm, m, ncols, lane, warp, false, true, nullptr, xs, accN, nullptr,
-                                                accT + j0);
+                                                accT + (j0 - r0));
                 else
                     consume_chunk<T, RPL, CONJ>(sm, m, ncols, lane, warp, true, fusedT, xs + (j0 - jw), xrs, accN,
                                                 fusedT ? tg + j0 : nullptr, nullptr);
@@ -600,7 +641,7 @@ __device__ __forceinline__ void tma_consumer(const MulArgs<T> &a, const bsm_slic
 #pragma unroll
         for (int w = 0; w < kFWarps; ++w) tot = El<T>::add(tot, red[w * kFMaxRows + t]);
         if (sl.flags & 1) {
-            const int32_t row = out.at(t);
+            const int32_t row = out.at(r0 + t);
             T v = El<T>::mul(a.alpha, tot);
             if (!a.beta_false) v = El<T>::add(v, El<T>::mul(a.beta, a.y[row]));
             a.y[row] = v;
@@ -619,9 +660,13 @@ __device__ __forceinline__ void tma_producer(const MulArgs<T> &a, const bsm_slic
         const bsm_contrib cb = a.contrib[ci];
         const int32_t m = cb.m;
         const int32_t cc = chunk_cols<T>(m);
+        const bool tform = (cb.form & 1) != 0;
+        const int32_t jlo = tform ? sl.r0 : 0;
+        const int32_t jhi = tform ? min(sl.r1, cb.out_len) : cb.n;
+        if (jhi <= jlo || m == 0) continue;
         const unsigned char *blk = reinterpret_cast<const unsigned char *>(a.arena + cb.off);
-        for (int32_t jw = 0; jw < cb.n; jw += kXsCap) {
-            const int32_t wend = min(cb.n, jw + kXsCap);
+        for (int32_t jw = jlo; jw < jhi; jw += kXsCap) {
+            const int32_t wend = min(jhi, jw + kXsCap);
             for (int32_t j0 = jw; j0 < wend; j0 += cc, ++q) {
                 const int32_t ncols = min(cc, wend - j0);
                 const uint32_t stage = q % kPStages;
@@ -636,7 +681,7 @@ __device__ __forceinline__ void tma_producer(const MulArgs<T> &a, const bsm_slic
     }
 }
 
-template <class T>
+template <class T, bool GEN>
 __global__ void __launch_bounds__(kPThreads, 2) sym_fused_tma_kernel(const MulArgs<T> a) {
     extern __shared__ __align__(128) unsigned char psm[];
     unsigned char *stages = psm;                                        // kPStages * kPStageBytes
@@ -658,21 +703,21 @@ __global__ void __launch_bounds__(kPThreads, 2) sym_fused_tma_kernel(const MulAr
         if (threadIdx.x == kFThreads) tma_producer<T>(a, sl, stages, full, empty);
         return;
     }
-    const int32_t L = sl.r1;
+    const int32_t L = sl.r1 - sl.r0;
     if (a.conj) {
         if (L <= 64)
-            tma_consumer<T, 2, true>(a, sl, stages, xs, xrs, accT, full, empty);
+            tma_consumer<T, 2, true, GEN>(a, sl, stages, xs, xrs, accT, full, empty);
         else if (L <= 128)
-            tma_consumer<T, 4, true>(a, sl, stages, xs, xrs, accT, full, empty);
+            tma_consumer<T, 4, true, GEN>(a, sl, stages, xs, xrs, accT, full, empty);
         else
-            tma_consumer<T, 8, true>(a, sl, stages, xs, xrs, accT, full, empty);
+            tma_consumer<T, 8, true, GEN>(a, sl, stages, xs, xrs, accT, full, empty);
     } else {
         if (L <= 64)
-            tma_consumer<T, 2, false>(a, sl, stages, xs, xrs, accT, full, empty);
+            tma_consumer<T, 2, false, GEN>(a, sl, stages, xs, xrs, accT, full, empty);
         else if (L <= 128)
-            tma_consumer<T, 4, false>(a, sl, stages, xs, xrs, accT, full, empty);
+            tma_consumer<T, 4, false, GEN>(a, sl, stages, xs, xrs, accT, full, empty);
         else
-            tma_consumer<T, 8, false>(a, sl, stages, xs, xrs, accT, full, empty);
+            tma_consumer<T, 8, false, GEN>(a, sl, stages, xs, xrs, accT, full, empty);
     }
 }
 
@@ -681,6 +726,301 @@ constexpr size_t fused_tma_smem_bytes() {
     return (size_t)kPStages * kPStageBytes + sizeof(T) * (size_t)(kXsCap + 2 * kFMaxRows) + 2 * kPStages * 8;
 }
 static_assert(kPStages * kPStageBytes >= kFWarps * kFMaxRows * 16, "reduction buffer must fit in the ring");
+
+// ---- warp-stream kernel ----------------------------------------------------------------------------
+// Small segments (<= 64 rows, blocks of <= 64 rows: VBCRS block rows, 32x32 BlockSparseMatrix blocks):
+// a CTA-wide pipeline would drain at every segment, so here every WARP owns a private shared-memory
+// byte ring and streams a long run of segments (a "work item") through it without ever synchronising
+// with another warp. Nothing on the critical path is a global load:
+//   * block data     cp.async.bulk (TMA, SASS UBLKCP) issued by lane 0 into the ring
+//   * x values       per-lane cp.async (LDGSTS) gathers into the ring right behind the block data,
+//                    completing on the SAME mbarrier (cp.async.mbarrier.arrive.noinc)
+//   * descriptors    bsm_wchunk records, bulk-copied in batches of 8 into a 32-entry descriptor ring
+// The ring placement (smem16) and the issue condition (lag) of every chunk are precomputed by the
+// packer — the chunk sequence of a work item is static — so up to ~20 KB per warp (8 warps per SM) are
+// in flight regardless of the block sizes. Lanes own rows (lane, lane+32):
+//   N-form  acc[r] += B[r, j] * x[j]           x[j] broadcast from shared memory
+//   T-form  t[j]   += sum_r B[r, j] * x[r]     four columns at a time, reduced by a halving butterfly
+//                                              (6 shuffles per 4 columns instead of 20)
+// At the last chunk of a segment the warp writes y (alpha/beta fused) or its partial vector.
+constexpr int kWWarps = 4;
+constexpr int kWRing = 16384;        // == plan.h kWRingBytes
+constexpr int kWNB = 16;             // == plan.h kWSlots
+constexpr int kWDBatch = 8;          // descriptors per bulk copy
+constexpr int kWDSlots = 4;          // descriptor ring = kWDSlots * kWDBatch records
+constexpr int kWSegMax = 64;
+
+template <class T>
+struct WarpArgs {
+    const unsigned char *arena;
+    const bsm_wchunk *chunks;
+    const int32_t *item_ptr;
+    const int32_t *pool;
+    const T *x;
+    T *y;
+    T *scratch;
+    T alpha, beta;
+    int32_t nitems;
+    int32_t beta_false;
+    int32_t conj;
+};
+
+struct WDesc {
+    int4 lo, hi;
+    __device__ __forceinline__ uint64_t src_bytes() const {
+        return ((((uint64_t)(((uint32_t)hi.x >> 8) & 0xffu)) << 32) | (uint64_t)(uint32_t)lo.x) << 4;
+    }
+    __device__ __forceinline__ uint32_t bytes() const { return ((uint32_t)lo.y & 0xffffu) << 4; }
+    __device__ __forceinline__ int32_t ncols() const { return (int32_t)((uint32_t)lo.y >> 16); }
+    __device__ __forceinline__ int32_t m() const { return (int32_t)((uint32_t)lo.z & 0xffu); }
+    __device__ __forceinline__ uint32_t flags() const { return ((uint32_t)lo.z >> 8) & 0xffu; }
+    __device__ __forceinline__ uint32_t delta() const { return ((uint32_t)lo.z >> 16) & 0xffu; }
+    __device__ __forceinline__ int32_t seg_len() const { return (int32_t)((uint32_t)lo.z >> 24); }
+    __device__ __forceinline__ int32_t x_ref() const { return lo.w; }
+    __device__ __forceinline__ int32_t out_col() const { return (int32_t)((uint32_t)hi.x & 0xffu); }
+    __device__ __forceinline__ uint32_t smem_off() const { return ((uint32_t)hi.x >> 16) << 4; }
+    __device__ __forceinline__ int32_t lag() const { return (int32_t)((uint32_t)hi.y & 0xffu); }
+    __device__ __forceinline__ int64_t out() const {
+        return (int64_t)(((uint64_t)(uint32_t)hi.w << 32) | (uint64_t)(uint32_t)hi.z);
+    }
+};
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_elem(void *dst_smem, const void *src) {
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "n"(BYTES)
+                     : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_plain(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// One chunk (nc whole columns of an m-row block, column-major in shared memory) of the warp-stream
+// kernel. TWO: the block has more than 32 rows, lanes also own row lane+32.
+template <class T, bool CONJ, bool TWO>
+__device__ __forceinline__ void wchunk_compute(const T *__restrict__ sm, const T *__restrict__ xin, int32_t m,
+                                               int32_t nc, bool tform, int32_t oc, int lane, T &acc0, T &acc1,
+                                               T *ts) {
+    const bool r0ok = lane < m, r1ok = TWO && (lane + 32) < m;
+    const T *p0 = sm + lane;
+    if (!tform) {
+        int32_t j = 0;
+        for (; j + 4 <= nc; j += 4) {
+            T v[4], w[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                v[c] = r0ok ? p0[(j + c) * m] : El<T>::zero();
+                if (TWO) w[c] = r1ok ? p0[(j + c) * m + 32] : El<T>::zero();
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const T xj = xin[j + c];
+                El<T>::fma(acc0, CONJ ? El<T>::conj(v[c]) : v[c], xj);
+                if (TWO) El<T>::fma(acc1, CONJ ? El<T>::conj(w[c]) : w[c], xj);
+            }
+        }
+        for (; j < nc; ++j) {
+            const T v = r0ok ? p0[j * m] : El<T>::zero();
+            const T xj = xin[j];
+            El<T>::fma(acc0, CONJ ? El<T>::conj(v) : v, xj);
+            if (TWO) {
+                const T w = r1ok ? p0[j * m + 32] : El<T>::zero();
+                El<T>::fma(acc1, CONJ ? El<T>::conj(w) : w, xj);
+            }
+        }
+    } else {
+        const T xa = r0ok ? xin[lane] : El<T>::zero();
+        const T xb = r1ok ? xin[lane + 32] : El<T>::zero();
+        for (int32_t j = 0; j < nc; j += 4) {
+            T p[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const bool cok = (j + c) < nc;
+                const T v = (cok && r0ok) ? p0[(j + c) * m] : El<T>::zero();
+                p[c] = El<T>::mul(CONJ ? El<T>::conj(v) : v, xa);
+                if (TWO) {
+                    const T w = (cok && r1ok) ? p0[(j + c) * m + 32] : El<T>::zero();
+                    El<T>::fma(p[c], CONJ ? El<T>::conj(w) : w, xb);
+                }
+            }
+            // halving butterfly: 4 columns -> lane bits (4,3) select the column
+            const bool h16 = (lane & 16) != 0;
+            T k0 = El<T>::add(h16 ? p[2] : p[0], El<T>::shfl_xor(h16 ? p[0] : p[2], 16));
+            T k1 = El<T>::add(h16 ? p[3] : p[1], El<T>::shfl_xor(h16 ? p[1] : p[3], 16));
+            const bool h8 = (lane & 8) != 0;
+            T k = El<T>::add(h8 ? k1 : k0, El<T>::shfl_xor(h8 ? k0 : k1, 8));
+            k = El<T>::add(k, El<T>::shfl_xor(k, 4));
+            k = El<T>::add(k, El<T>::shfl_xor(k, 2));
+            k = El<T>::add(k, El<T>::shfl_xor(k, 1));
+            const int32_t col = j + (lane >> 3);
+            if ((lane & 7) == 0 && col < nc) ts[oc + col] = El<T>::add(ts[oc + col], k);
+        }
+    }
+}
+
+template <class T, bool CONJ>
+__device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned char *ring, const int4 *dring,
+                                                 T *xs, T *ts, uint64_t *full, uint64_t *dbar, int32_t q0,
+                                                 int32_t n) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t policy = l2_evict_first_policy();
+    const int32_t nbatch = (n + kWDBatch - 1) / kWDBatch;
+    auto load_batch = [&](int32_t b) {  // lane 0 only
+        const uint32_t cnt = (uint32_t)min(kWDBatch, n - b * kWDBatch);
+        uint64_t *bar = &dbar[b & (kWDSlots - 1)];
+        mbar_arrive_expect_tx(bar, cnt * 32u);
+        bulk_g2s_plain(const_cast<int4 *>(dring) + (b & (kWDSlots - 1)) * kWDBatch * 2,
+                       a.chunks + q0 + b * kWDBatch, cnt * 32u, bar);
+    };
+    auto desc_at = [&](int32_t i) {
+        WDesc d;
+        const int4 *p = dring + (i & (kWDSlots * kWDBatch - 1)) * 2;
+        d.lo = p[0];
+        d.hi = p[1];
+        return d;
+    };
+    if (lane == 0)
+        for (int32_t b = 0; b < kWDSlots && b < nbatch; ++b) load_batch(b);
+    int32_t ii = 0, ibatch = -1, done = 0;
+    // issues every chunk whose ring space is free (warp-uniform; lane 0 drives the TMA, all lanes gather x)
+    auto issue_ready = [&]() {
+        while (ii < n) {
+            const int32_t b = ii / kWDBatch;
+            if (b != ibatch) {
+                mbar_wait(&dbar[b & (kWDSlots - 1)], (uint32_t)((b / kWDSlots) & 1));
+                ibatch = b;
+            }
+            const WDesc d = desc_at(ii);
+            if (ii - d.lag() > done) break;
+            uint64_t *bar = &full[ii & (kWNB - 1)];
+            unsigned char *dst = ring + d.smem_off();
+            const uint32_t bytes = d.bytes();
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar, bytes);
+                bulk_g2s(dst, a.arena + d.src_bytes(), bytes, bar, policy);
+            }
+            const uint32_t fl = d.flags();
+            if (!(fl & 2u)) {
+                const int32_t cnt = (fl & 1u) ? d.m() : d.ncols();
+                const T *src = a.x + d.x_ref();
+                T *xd = reinterpret_cast<T *>(dst + bytes);
+                if (lane < cnt) cp_async_elem<(int)sizeof(T)>(xd + lane, src + lane);
+                if (lane + 32 < cnt) cp_async_elem<(int)sizeof(T)>(xd + lane + 32, src + lane + 32);
+            }
+            cp_async_mbar_arrive_noinc(bar);
+            ++ii;
+        }
+    };
+    issue_ready();
+    T acc0 = El<T>::zero(), acc1 = El<T>::zero();
+    int32_t cbatch = -1;
+    for (int32_t ci = 0; ci < n; ++ci) {
+        const int32_t b = ci / kWDBatch;
+        if (b != cbatch) {
+            mbar_wait(&dbar[b & (kWDSlots - 1)], (uint32_t)((b / kWDSlots) & 1));
+            cbatch = b;
+            // batch b-1 is behind both cursors: its slot takes batch b+3
+            if (b >= 1 && b + kWDSlots - 1 < nbatch && lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                load_batch(b + kWDSlots - 1);
+            }
+        }
+        const WDesc d0 = desc_at(ci);
+        const uint32_t fl = d0.flags();
+        const int32_t m = d0.m(), nc = d0.ncols();
+        const bool tform = (fl & 1u) != 0;
+        const unsigned char *cbase = ring + d0.smem_off();
+        const T *xin = reinterpret_cast<const T *>(cbase + d0.bytes());
+        if (fl & 8u) {  // first chunk of a segment
+            acc0 = El<T>::zero();
+            acc1 = El<T>::zero();
+            ts[lane] = El<T>::zero();
+            ts[lane + 32] = El<T>::zero();
+        }
+        if (fl & 2u) {
+            // arbitrary index vector: gather x through the pool into the warp's staging array
+            const int32_t cnt = tform ? m : nc;
+            xs[lane] = (lane < cnt) ? a.x[__ldg(a.pool + d0.x_ref() + lane)] : El<T>::zero();
+            xs[lane + 32] = (lane + 32 < cnt) ? a.x[__ldg(a.pool + d0.x_ref() + lane + 32)] : El<T>::zero();
+            xin = xs;
+        }
+        __syncwarp();
+        mbar_wait(&full[ci & (kWNB - 1)], (uint32_t)((ci / kWNB) & 1));
+        const T *sm = reinterpret_cast<const T *>(cbase + d0.delta());
+        if (m > 32)
+            wchunk_compute<T, CONJ, true>(sm, xin, m, nc, tform, d0.out_col(), lane, acc0, acc1, ts);
+        else
+            wchunk_compute<T, CONJ, false>(sm, xin, m, nc, tform, d0.out_col(), lane, acc0, acc1, ts);
+        __syncwarp();
+        done = ci + 1;
+        if (fl & 16u) {  // last chunk of the segment: write the outputs
+            const int32_t L = d0.seg_len();
+            const int64_t o = d0.out();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int32_t r = lane + 32 * h;
+                if (r < L) {
+                    const T tot = El<T>::add(h ? acc1 : acc0, ts[r]);
+                    if (fl & 32u) {
+                        const int32_t row = (fl & 4u) ? __ldg(a.pool + o + r) : (int32_t)o + r;
+                        T v = El<T>::mul(a.alpha, tot);
+                        if (!a.beta_false) v = El<T>::add(v, El<T>::mul(a.beta, a.y[row]));
+                        a.y[row] = v;
+                    } else {
+                        a.scratch[o + r] = tot;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_ready();
+    }
+}
+
+template <class T>
+__host__ __device__ constexpr size_t stream_warp_smem_per_warp() {
+    return (size_t)kWRing + (size_t)kWDSlots * kWDBatch * 32 + 2 * kWSegMax * sizeof(T) + 8 * (kWNB + kWDSlots);
+}
+template <class T>
+constexpr size_t stream_warp_smem_bytes() {
+    return kWWarps * stream_warp_smem_per_warp<T>();
+}
+
+template <class T>
+__global__ void __launch_bounds__(kWWarps * 32) stream_warp_kernel(const WarpArgs<T> a) {
+    extern __shared__ __align__(128) unsigned char wsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int32_t item = blockIdx.x * kWWarps + warp;
+    if (item >= a.nitems) return;
+    unsigned char *base = wsm + warp * stream_warp_smem_per_warp<T>();
+    unsigned char *ring = base;
+    const int4 *dring = reinterpret_cast<const int4 *>(base + kWRing);
+    T *xs = reinterpret_cast<T *>(base + kWRing + kWDSlots * kWDBatch * 32);
+    T *ts = xs + kWSegMax;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ts + kWSegMax);
+    uint64_t *dbar = full + kWNB;
+    if (lane == 0) {
+        for (int i = 0; i < kWNB; ++i) mbar_init(&full[i], 33);  // lane 0's expect_tx + 32 cp.async arrivals
+        for (int i = 0; i < kWDSlots; ++i) mbar_init(&dbar[i], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    const int32_t q0 = __ldg(a.item_ptr + item), q1 = __ldg(a.item_ptr + item + 1);
+    if (q0 >= q1) return;
+    if (a.conj)
+        stream_warp_body<T, true>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0);
+    else
+        stream_warp_body<T, false>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0);
+}
 
 template <class T>
 struct FinalizeArgs {

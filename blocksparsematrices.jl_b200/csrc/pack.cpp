@@ -191,8 +191,38 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
             if (P.contrib[c].m % V != 0) vec_ok = false;
         }
         if (L % V != 0) vec_ok = false;
-        if (pp.fused && L <= kFusedMaxRows) {
-            // one work item for the whole segment: the fused kernel keeps all its rows in registers
+        // stream plans: classify the segment for the TMA-staged kernels
+        bool any_fuse = false, all_t = true, t_ok = true, small_ok = true;
+        int64_t entries = 0;
+        for (int64_t c = P.group_ptr[g]; c < P.group_ptr[g + 1]; ++c) {
+            const bsm_contrib &cb = P.contrib[c];
+            entries += (int64_t)cb.m * cb.n;
+            if (contrib_tset[(size_t)c] >= 0) any_fuse = true;
+            if (cb.form & kFormT) {
+                if (cb.m > kFusedMaxTRows) t_ok = false;
+            } else {
+                all_t = false;
+            }
+            if (cb.m > kWarpMaxRows) small_ok = false;
+        }
+        if (pp.fused && pp.warp_stream && L <= kWarpMaxRows && small_ok && !any_fuse && entries > 0 &&
+            S.pool.size() < (size_t)0x7fffffff) {
+            // whole segment streamed by ONE warp of stream_warp_kernel
+            Tmp t;
+            t.s.out_set = gset[g];
+            t.s.r0 = 0;
+            t.s.r1 = (int32_t)L;
+            t.s.c_begin = (int32_t)P.group_ptr[g];
+            t.s.c_end = (int32_t)P.group_ptr[g + 1];
+            t.s.flags = (P.group_direct[g] ? kSliceDirect : 0) | kSliceWarp;
+            t.s.scratch_off = 0;
+            t.work = W;
+            t.order = (int64_t)tmp.size();
+            tmp.push_back(t);
+            continue;
+        }
+        if (pp.fused && L <= kFusedMaxRows && t_ok) {
+            // one work item for the whole segment: the CTA kernel keeps all its rows in registers
             Tmp t;
             t.s.out_set = gset[g];
             t.s.r0 = 0;
@@ -204,6 +234,29 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
             t.work = W;
             t.order = (int64_t)tmp.size();
             tmp.push_back(t);
+            continue;
+        }
+        if (pp.fused && all_t && t_ok && !any_fuse) {
+            // long segment fed by T-form contributions only: a sub-range of outputs is a run of whole
+            // (contiguous) block columns, so the CTA kernel streams it like a short segment
+            int64_t pieces = (L + kFusedMaxRows - 1) / kFusedMaxRows;
+            pieces = std::max(pieces, std::min((W + pp.work_target_bytes - 1) / pp.work_target_bytes,
+                                               std::max<int64_t>(1, L / 16)));
+            int64_t ps = (L + pieces - 1) / pieces;
+            ps = std::min<int64_t>((ps + 3) / 4 * 4, kFusedMaxRows);
+            for (int64_t r0 = 0; r0 < L; r0 += ps) {
+                Tmp t;
+                t.s.out_set = gset[g];
+                t.s.r0 = (int32_t)r0;
+                t.s.r1 = (int32_t)std::min(L, r0 + ps);
+                t.s.c_begin = (int32_t)P.group_ptr[g];
+                t.s.c_end = (int32_t)P.group_ptr[g + 1];
+                t.s.flags = (P.group_direct[g] ? kSliceDirect : 0) | kSliceFused;
+                t.s.scratch_off = 0;
+                t.work = W * (t.s.r1 - t.s.r0) / L;
+                t.order = (int64_t)tmp.size();
+                tmp.push_back(t);
+            }
             continue;
         }
         int64_t pieces = (L + kMaxSliceHeight - 1) / kMaxSliceHeight;
@@ -291,16 +344,135 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
         }
     }
 
-    // 6. schedule: fused slices first, heaviest first inside each class (stable)
-    std::stable_sort(tmp.begin(), tmp.end(), [](const Tmp &a, const Tmp &b) {
-        const int fa = (a.s.flags & kSliceFused) != 0, fb = (b.s.flags & kSliceFused) != 0;
-        if (fa != fb) return fa > fb;
+    // 6. schedule: CTA-kernel slices first (heaviest first), then the warp-stream slices in creation
+    //    order (= arena order, so every warp streams a contiguous run of HBM), then the gather slices
+    //    (heaviest first); stable
+    auto cls = [](const Tmp &t) { return (t.s.flags & kSliceFused) ? 0 : (t.s.flags & kSliceWarp) ? 1 : 2; };
+    std::stable_sort(tmp.begin(), tmp.end(), [&](const Tmp &a, const Tmp &b) {
+        const int ca = cls(a), cb = cls(b);
+        if (ca != cb) return ca < cb;
+        if (ca == 1) return false;
         return a.work > b.work;
     });
     P.slices.reserve(tmp.size());
     for (const auto &t : tmp) {
         P.slices.push_back(t.s);
+        if (t.s.flags & kSliceFused) {
+            const int32_t Ls = t.s.r1 - t.s.r0;
+            const int32_t lane_rows = Ls <= 64 ? 64 : Ls <= 128 ? 128 : 256;  // rows held by the lanes (32 * RPL)
+            if (t.s.r0 > 0 || t.s.r1 < S.len[t.s.out_set]) P.fused_general = true;
+            for (int32_t c = t.s.c_begin; c < t.s.c_end; ++c)
+                if ((P.contrib[c].form & kFormT) && P.contrib[c].m > lane_rows) P.fused_general = true;
+        }
         if (t.s.flags & kSliceFused) P.n_fused_slices++;
+        if (t.s.flags & kSliceWarp) P.n_warp_slices++;
+    }
+
+    // 7. chunk stream of the warp slices: every chunk is one bulk copy of whole block columns and
+    //    carries the resolved x / y positions, so the consuming warp never chases a table
+    if (P.n_warp_slices > 0) {
+        int64_t total = 0;
+        for (int64_t i = P.n_fused_slices; i < P.n_fused_slices + P.n_warp_slices; ++i)
+            for (int32_t c = P.slices[i].c_begin; c < P.slices[i].c_end; ++c)
+                total += (int64_t)P.contrib[c].m * P.contrib[c].n * s;
+        int64_t target = pp.witem_bytes;
+        if (target <= 0) target = std::min<int64_t>(1 << 20, std::max<int64_t>(16 << 10, total / (148 * 8 * 6)));
+        P.witem_ptr.push_back(0);
+        int64_t item_bytes = 0;
+        for (int64_t i = P.n_fused_slices; i < P.n_fused_slices + P.n_warp_slices; ++i) {
+            const bsm_slice &sl = P.slices[i];
+            const int64_t L = S.len[sl.out_set];
+            const size_t first = P.wchunk.size();
+            for (int32_t c = sl.c_begin; c < sl.c_end; ++c) {
+                const bsm_contrib &cb = P.contrib[c];
+                if (cb.m == 0 || cb.n == 0) continue;
+                const bool tf = (cb.form & kFormT) != 0;
+                const int64_t colbytes = (int64_t)cb.m * s;
+                int64_t nch = ((int64_t)cb.n * colbytes + kWChunkBytes - 1) / kWChunkBytes;
+                nch = std::max<int64_t>(nch, (cb.n + kWMaxCols - 1) / kWMaxCols);
+                int64_t cc = (cb.n + nch - 1) / nch;
+                cc = (cc + 3) / 4 * 4;
+                cc = std::min<int64_t>(cc, std::min<int64_t>(kWMaxCols, kWChunkBytes / colbytes));
+                cc = std::max<int64_t>(cc / 4 * 4, 1);
+                for (int64_t j0 = 0; j0 < cb.n; j0 += cc) {
+                    const int64_t nc = std::min<int64_t>(cc, cb.n - j0);
+                    const int64_t b0 = cb.off * s + j0 * colbytes;      // first byte of the chunk
+                    const int64_t a0 = b0 & ~(int64_t)15;
+                    const int64_t bytes = ((b0 - a0) + nc * colbytes + 15) & ~(int64_t)15;
+                    bsm_wchunk w;
+                    std::memset(&w, 0, sizeof(w));
+                    w.src16 = (uint32_t)((a0 >> 4) & 0xffffffffll);
+                    w.src16_hi = (uint8_t)((a0 >> 4) >> 32);
+                    w.bytes16 = (uint16_t)(bytes >> 4);
+                    w.ncols = (uint16_t)nc;
+                    w.m = (uint8_t)cb.m;
+                    w.delta = (uint8_t)(b0 - a0);
+                    w.seg_len = (uint8_t)L;
+                    w.flags = (uint8_t)(tf ? kWcT : 0);
+                    const bool xpool = S.start[cb.in_set] < 0;
+                    if (xpool) w.flags |= kWcXPool;
+                    const int64_t xbase = xpool ? S.pool_off[cb.in_set] : (int64_t)S.start[cb.in_set];
+                    w.x_ref = (int32_t)(tf ? xbase : xbase + j0);
+                    w.out_col = (uint8_t)(tf ? j0 : 0);
+                    P.wchunk.push_back(w);
+                    item_bytes += bytes;
+                }
+            }
+            if (P.wchunk.size() == first) return "warp-stream segment without data";
+            bsm_wchunk &wb = P.wchunk[first];
+            bsm_wchunk &we = P.wchunk.back();
+            wb.flags |= kWcSegBegin;
+            we.flags |= kWcSegEnd;
+            if (sl.flags & kSliceDirect) {
+                we.flags |= kWcDirect;
+                if (S.start[sl.out_set] < 0) {
+                    we.flags |= kWcOutPool;
+                    we.out = S.pool_off[sl.out_set];
+                } else {
+                    we.out = S.start[sl.out_set];
+                }
+            } else {
+                we.out = sl.scratch_off;
+            }
+            if (item_bytes >= target) {
+                P.witem_ptr.push_back((int32_t)P.wchunk.size());
+                item_bytes = 0;
+            }
+        }
+        if (P.witem_ptr.back() != (int32_t)P.wchunk.size()) P.witem_ptr.push_back((int32_t)P.wchunk.size());
+        // static shared-memory schedule of every work item: chunks are placed in a circular byte
+        // buffer in issue order; a chunk that does not fit waits for the oldest live chunks
+        for (size_t it = 0; it + 1 < P.witem_ptr.size(); ++it) {
+            const int32_t q0 = P.witem_ptr[it], q1 = P.witem_ptr[it + 1];
+            int64_t head = 0;            // next free byte
+            int32_t oldest = q0;         // oldest live (issued, not yet consumed) chunk
+            for (int32_t q = q0; q < q1; ++q) {
+                bsm_wchunk &w = P.wchunk[(size_t)q];
+                const int64_t cnt = (w.flags & kWcT) ? w.m : w.ncols;
+                const int64_t foot = (int64_t)w.bytes16 * 16 + ((cnt * s + 15) & ~(int64_t)15);
+                if (foot > kWRingBytes) return "warp-stream chunk larger than the ring";
+                for (;;) {
+                    // live region: from the oldest live chunk's offset to head (circular)
+                    bool fits;
+                    if (oldest == q) {
+                        head = 0;
+                        fits = true;
+                    } else {
+                        const int64_t tail = (int64_t)P.wchunk[(size_t)oldest].smem16 * 16;
+                        if (head > tail)
+                            fits = (head + foot <= kWRingBytes) || (foot <= tail);
+                        else
+                            fits = head + foot <= tail;
+                        if (fits && head > tail && head + foot > kWRingBytes) head = 0;
+                    }
+                    if (fits && q - oldest < kWSlots - 1) break;
+                    ++oldest;            // wait for one more chunk to be consumed
+                }
+                w.smem16 = (uint16_t)(head >> 4);
+                w.lag = (uint8_t)(q - oldest);
+                head += foot;
+            }
+        }
     }
     return std::string();
 }

@@ -26,11 +26,21 @@ namespace bsm {
 
 static_assert(sizeof(bsm_contrib) == 32, "bsm_contrib must be 32 bytes");
 static_assert(sizeof(bsm_slice) == 32, "bsm_slice must be 32 bytes");
+static_assert(sizeof(bsm_wchunk) == 32, "bsm_wchunk must be 32 bytes");
 
 constexpr int kSliceDirect = 1;
 constexpr int kSliceVecOk = 2;
 constexpr int kSliceFused = 4;          // handled by sym_fused_kernel (whole segment, <= kFusedMaxRows rows)
+constexpr int kSliceWarp = 8;           // handled by stream_warp_kernel (whole segment, <= kWarpMaxRows rows)
 constexpr int kFusedMaxRows = 256;
+constexpr int kFusedMaxTRows = 1024;    // tallest T-form block the CTA kernel stages (x window in shared memory)
+constexpr int kWarpMaxRows = 64;        // segment length and block height limit of the warp-stream kernel
+constexpr int kWChunkBytes = 4096;      // largest block payload of one warp-stream chunk
+constexpr int kWRingBytes = 16384;      // shared-memory byte ring of one warp (chunks + their x values)
+constexpr int kWSlots = 16;             // mbarrier slots of one warp: chunks in flight + the one being consumed
+constexpr int kWMaxCols = 64;           // columns per warp-stream chunk (two prefetched x values per lane)
+// bsm_wchunk.flags
+constexpr int kWcT = 1, kWcXPool = 2, kWcOutPool = 4, kWcSegBegin = 8, kWcSegEnd = 16, kWcDirect = 32;
 constexpr int kFormT = 1;               // bsm_contrib.form bit0: T-form
 constexpr int kFormFusedT = 2;          // bit1: also emits the transposed partial of the same block
 constexpr int kMaxSliceHeight = 128;   // outputs per work item (one CTA of 128 threads)
@@ -83,6 +93,10 @@ struct HostPlan {
     std::vector<int64_t> contrib_toff;  // scratch offset of the fused transposed partial, -1 if none
     std::vector<bsm_slice> slices;      // fused slices first, each class sorted by decreasing work
     int64_t n_fused_slices = 0;
+    bool fused_general = false;         // some CTA-kernel slice is a column sub-range or holds a tall T-form block
+    int64_t n_warp_slices = 0;          // follow the fused slices; the rest go to gather_gemv_kernel
+    std::vector<bsm_wchunk> wchunk;     // chunk stream of the warp slices, in slice order
+    std::vector<int32_t> witem_ptr;     // warp work items: chunk ranges cut at segment boundaries
     std::vector<int32_t> gather_rows;
     std::vector<int64_t> gather_ptr;
     std::vector<int64_t> gather_pos;
@@ -110,7 +124,11 @@ struct HostMatrix {
 struct PlanParams {
     int64_t own_lo = 0, own_hi = -1;   // owned output range, hi < 0: everything
     int64_t work_target_bytes = 512 << 10;
-    bool fused = false;                // segments of <= kFusedMaxRows rows go to the fused kernel, unsplit
+    bool fused = false;                // stream plan: segments of <= kFusedMaxRows rows go to the TMA-staged
+                                       // kernels (CTA kernel, or warp-stream kernel when <= kWarpMaxRows), unsplit
+    bool warp_stream = true;           // short segments may go to the warp-stream kernel (off for symmetric
+                                       // matrices: their leaf segments stay with the CTA kernel, one launch)
+    int64_t witem_bytes = 0;           // target bytes per warp work item (0: derived from the total)
 };
 
 // Lays the blocks out in the arena (fills block_off, arena_elems, stored).

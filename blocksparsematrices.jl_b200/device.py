@@ -161,6 +161,15 @@ class DeviceMatrix:
     def launch_count(self, op="N") -> int:
         return int(L.lib().bsm_launch_count(self._h, _OPS[op]))
 
+    def plan_stats(self, op="N") -> dict:
+        """Work split of the plan used for `op` between the three multiply kernels."""
+        out = np.zeros(10, np.int64)
+        L.check(L.lib().bsm_plan_stats(self._h, _OPS[op], _i64p(out)))
+        names = ("sym_fused_tma_kernel", "stream_warp_kernel", "gather_gemv_kernel")
+        return {"slices": dict(zip(names, out[0:3].tolist())), "bytes": dict(zip(names, out[3:6].tolist())),
+                "warp_items": int(out[6]), "warp_chunks": int(out[7]), "scratch_elems": int(out[8]),
+                "finalized_rows": int(out[9])}
+
     def set_profiling(self, on: bool):
         L.check(L.lib().bsm_set_profiling(self._h, int(on)))
 
@@ -188,6 +197,8 @@ class DeviceMatrix:
             dt = CONTRIB_DTYPE
         elif table == L.TAB_SLICE:
             dt = SLICE_DTYPE
+        elif table == L.TAB_WCHUNK:
+            dt = WCHUNK_DTYPE
         else:
             dt = np.dtype(np.int32)
         out = np.zeros(cnt, dt)
@@ -254,7 +265,11 @@ CONTRIB_DTYPE = np.dtype([("off", np.int64), ("m", np.int32), ("n", np.int32), (
                           ("form", np.int32), ("out_len", np.int32), ("block", np.int32)])
 SLICE_DTYPE = np.dtype([("out_set", np.int32), ("r0", np.int32), ("r1", np.int32), ("c_begin", np.int32),
                         ("c_end", np.int32), ("flags", np.int32), ("scratch_off", np.int64)])
-assert CONTRIB_DTYPE.itemsize == 32 and SLICE_DTYPE.itemsize == 32
+WCHUNK_DTYPE = np.dtype([("src16", np.uint32), ("bytes16", np.uint16), ("ncols", np.uint16), ("m", np.uint8),
+                         ("flags", np.uint8), ("delta", np.uint8), ("seg_len", np.uint8), ("x_ref", np.int32),
+                         ("out_col", np.uint8), ("src16_hi", np.uint8), ("smem16", np.uint16), ("lag", np.uint8),
+                         ("reserved", np.uint8, (3,)), ("out", np.int64)])
+assert CONTRIB_DTYPE.itemsize == 32 and SLICE_DTYPE.itemsize == 32 and WCHUNK_DTYPE.itemsize == 32
 
 
 def _is_torch(x) -> bool:

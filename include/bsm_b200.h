@@ -148,6 +148,11 @@ int bsm_work(bsm_handle h, int op, int64_t nrhs, int beta_used, double *bytes, d
              double *index_table_bytes);
 /* Number of kernels one bsm_mul launches for `op` with the current variant (nrhs = 1). */
 int bsm_launch_count(bsm_handle h, int op);
+/* Work split of the plan bsm_mul uses for `op` with the current variant. out[0..2] = slices handled by
+ * the CTA-stream kernel (sym_fused_tma_kernel), the warp-stream kernel (stream_warp_kernel) and the
+ * gather kernel (gather_gemv_kernel); out[3..5] = block bytes each of them streams; out[6] = warp work
+ * items; out[7] = warp-stream chunks; out[8] = scratch elements; out[9] = rows finalised by the gather pass. */
+int bsm_plan_stats(bsm_handle h, int op, int64_t out[10]);
 
 /* ---- table export (bit-exact packing checks) ---------------------------------------------- */
 typedef enum {
@@ -169,7 +174,9 @@ typedef enum {
     BSM_TAB_GROUP_PTR = 13,   /* int64: CSR over contributions per output segment ("block-row pointer";
                                  for plan 1 this is the transposed index) */
     BSM_TAB_GROUP_SET = 14,   /* int32: index-set id of every output segment */
-    BSM_TAB_CONTRIB_TOFF = 15 /* int64: scratch offset of the fused transposed partial of a contribution, -1 if none */
+    BSM_TAB_CONTRIB_TOFF = 15,/* int64: scratch offset of the fused transposed partial of a contribution, -1 if none */
+    BSM_TAB_WCHUNK = 16,      /* bsm_wchunk records: the chunk stream of the warp-stream kernel (plans 2/3) */
+    BSM_TAB_WITEM_PTR = 17    /* int32: chunk range [ptr[i], ptr[i+1]) of warp work item i */
 } bsm_table;
 
 /* 32-byte device records (exported verbatim). */
@@ -190,9 +197,36 @@ typedef struct {
     int32_t r0, r1;      /* output sub-range [r0, r1) of the segment handled by this work item */
     int32_t c_begin, c_end; /* contributions [c_begin, c_end) */
     int32_t flags;       /* bit0: direct (writes y), else partial sums to scratch; bit1: vector loads ok;
-                            bit2: whole segment, handled by the fused symmetric kernel */
+                            bit2: handled by the TMA-staged CTA kernel (whole segment of <= 256 rows, or a
+                            column sub-range of an all-T-form segment); bit3: whole segment of <= 64 rows,
+                            handled by the warp-stream kernel through the bsm_wchunk stream */
     int64_t scratch_off; /* element offset of the partial vector when not direct */
 } bsm_slice;
+
+/* One TMA bulk copy of the warp-stream kernel: `ncols` whole columns of one block (m <= 64 rows), with
+ * everything the consuming warp needs so that it never chases a pointer on its critical path. The
+ * shared-memory placement of every chunk in the warp's byte ring is decided by the packer (the chunk
+ * sequence of a work item is static): the chunk occupies [smem16*16, smem16*16 + bytes16*16 + x area)
+ * and may be issued once all but `lag` of the chunks before it in its work item have been consumed. */
+typedef struct {
+    uint32_t src16;      /* arena byte offset / 16 of the copy (start rounded down to 16 bytes), low 32 bits */
+    uint16_t bytes16;    /* copy size / 16 */
+    uint16_t ncols;      /* whole columns in the chunk (<= 64) */
+    uint8_t m;           /* rows of the block (<= 64) */
+    uint8_t flags;       /* bit0 T-form; bit1 x_ref is a pool offset; bit2 out is a pool offset;
+                            bit3 first chunk of its segment; bit4 last chunk of its segment; bit5 direct */
+    uint8_t delta;       /* byte offset of the first column inside the copy (0..15) */
+    uint8_t seg_len;     /* rows of the output segment (<= 64) */
+    int32_t x_ref;       /* N-form: position in x of the chunk's first column; T-form: of the block's
+                            first row (an index into x, or into the index pool when bit1) */
+    uint8_t out_col;     /* T-form: position of the chunk's first column inside the segment */
+    uint8_t src16_hi;    /* bits 32..39 of the 16-byte unit offset */
+    uint16_t smem16;     /* offset / 16 of the chunk in the warp's shared-memory ring */
+    uint8_t lag;         /* chunk i of a work item may be issued once i - lag chunks have been consumed */
+    uint8_t reserved[3];
+    int64_t out;         /* last chunk of a segment: first output row (index into y, or pool offset when
+                            bit2) if direct, else element offset of the partial vector in the scratch */
+} bsm_wchunk;
 
 int64_t bsm_table_count(bsm_handle h, int table, int plan); /* number of elements/records, <0 on error */
 int bsm_table_copy(bsm_handle h, int table, int plan, void *dst, int64_t dst_bytes);

@@ -65,15 +65,26 @@ def run_plan(A, D, op, x, alpha=1.0, beta=0.0, beta_false=True, y=None, own=None
     for k in range(1, len(slices)):      # fused slices come first
         assert not ((slices[k]["flags"] & 4) and not (slices[k - 1]["flags"] & 4))
     written = np.zeros(nout, np.int32)
+    cls = [0 if (s["flags"] & 4) else 1 if (s["flags"] & 8) else 2 for s in slices]
+    assert cls == sorted(cls), "slice classes must be ordered: CTA-stream, warp-stream, gather"
+    run_warp_stream(D, plan, arena, S, slices, x, y, scratch, written, conj, alpha, beta, beta_false, dt)
     for s in slices:
+        if s["flags"] & 8:
+            continue            # executed from the chunk stream above
         r0, r1 = int(s["r0"]), int(s["r1"])
         h = r1 - r0
         fused = bool(s["flags"] & 4)
-        assert 0 < h <= (256 if fused else 128) and (r0 == 0 or not fused)
+        assert 0 < h <= (256 if fused else 128)
+        if fused and r0 > 0 or (fused and r1 < S.len[s["out_set"]]):
+            # column sub-range of a long segment: only T-form blocks of <= 1024 rows
+            assert all((contrib[ci]["form"] & 3) == 1 and contrib[ci]["m"] <= 1024
+                       for ci in range(s["c_begin"], s["c_end"]))
         acc = np.zeros(h, dt)
         for ci in range(s["c_begin"], s["c_end"]):
             c = contrib[ci]
             m, n = int(c["m"]), int(c["n"])
+            if fused and (c["form"] & 1):
+                assert m <= 1024       # x window of the CTA kernel
             B = arena[c["off"]:c["off"] + m * n].reshape((m, n), order="F")
             if conj:
                 B = B.conj()
@@ -122,3 +133,88 @@ def run_plan(A, D, op, x, alpha=1.0, beta=0.0, beta_false=True, y=None, own=None
     assert np.all(covered[lo:hi]), "an owned row is neither written directly nor finalised"
     assert not np.any(covered[:lo]) and not np.any(covered[hi:]), "a row outside the slab was written"
     return y
+
+
+def run_warp_stream(D, plan, arena, S, slices, x, y, scratch, written, conj, alpha, beta, beta_false, dt):
+    """Executes the bsm_wchunk stream exactly as stream_warp_kernel does: per work item, chunk by chunk,
+    reading the arena BYTES the bulk copy would fetch."""
+    chunks = D.table(L.TAB_WCHUNK, plan)
+    iptr = D.table(L.TAB_WITEM_PTR, plan)
+    wsl = [s for s in slices if s["flags"] & 8]
+    if not wsl:
+        assert chunks.size == 0 and iptr.size == 0
+        return
+    assert iptr[0] == 0 and iptr[-1] == len(chunks) and np.all(np.diff(iptr) > 0)
+    raw = arena.view(np.uint8)
+    isz = arena.dtype.itemsize
+    nseg = 0
+    for it in range(len(iptr) - 1):
+        acc = None
+        check_ring_schedule(chunks[iptr[it]:iptr[it + 1]], isz)
+        for q in range(iptr[it], iptr[it + 1]):
+            c = chunks[q]
+            fl, m, nc, Lseg = int(c["flags"]), int(c["m"]), int(c["ncols"]), int(c["seg_len"])
+            if fl & 8:
+                assert acc is None
+                acc = np.zeros(Lseg, dt)
+            assert acc is not None, "work item must start at a segment boundary"
+            assert 0 < m <= 64 and 0 < nc <= 64 and Lseg <= 64
+            src = ((int(c["src16_hi"]) << 32) | int(c["src16"])) * 16
+            nbytes = int(c["bytes16"]) * 16
+            assert nbytes <= 4096 + 16 and int(c["delta"]) + m * nc * isz <= nbytes
+            buf = raw[src:src + nbytes]
+            Bc = buf[int(c["delta"]):int(c["delta"]) + m * nc * isz].view(arena.dtype).reshape((m, nc), order="F")
+            if conj:
+                Bc = Bc.conj()
+            cnt = m if (fl & 1) else nc
+            pos = np.arange(c["x_ref"], c["x_ref"] + cnt)
+            xi = x[S.pool[pos]] if (fl & 2) else x[pos]
+            if fl & 1:
+                oc = int(c["out_col"])
+                acc[oc:oc + nc] += Bc.T @ xi
+            else:
+                acc[:m] += Bc @ xi
+            if fl & 16:
+                o = int(c["out"])
+                if fl & 32:
+                    rows = S.pool[o:o + Lseg].astype(np.int64) if (fl & 4) else np.arange(o, o + Lseg)
+                    assert np.all(written[rows] == 0), "direct rows written twice"
+                    written[rows] += 1
+                    y[rows] = alpha * acc + (0 if beta_false else beta * y[rows])
+                else:
+                    assert np.all(np.isnan(scratch[o:o + Lseg]))
+                    scratch[o:o + Lseg] = acc
+                acc = None
+                nseg += 1
+        assert acc is None, "work item must end at a segment boundary"
+    assert nseg == len(wsl)
+    for s in wsl:
+        assert s["r0"] == 0 and s["r1"] == S.len[s["out_set"]] <= 64
+
+
+RING_BYTES, RING_SLOTS = 16384, 16
+
+
+def check_ring_schedule(ch, isz):
+    """Replays the issue / consume order of one warp work item: chunk i is issued as soon as i - lag
+    chunks have been consumed; its ring region must not overlap any chunk still live, and at most
+    RING_SLOTS chunks (one mbarrier each) may be live."""
+    n = len(ch)
+    foot = ch["bytes16"].astype(np.int64) * 16
+    cnt = np.where(ch["flags"] & 1, ch["m"], ch["ncols"]).astype(np.int64)
+    foot += (cnt * isz + 15) // 16 * 16
+    off = ch["smem16"].astype(np.int64) * 16
+    assert np.all(off + foot <= RING_BYTES)
+    lag = ch["lag"].astype(np.int64)
+    assert np.all(lag <= np.arange(n)) and np.all(lag < RING_SLOTS)
+    ii, live = 0, []
+    for done in range(n + 1):          # state after `done` chunks have been consumed
+        live = [k for k in live if k >= done]
+        while ii < n and ii - lag[ii] <= done:
+            for k in live:
+                assert off[ii] + foot[ii] <= off[k] or off[k] + foot[k] <= off[ii], "ring regions overlap"
+            live.append(ii)
+            assert len(live) <= RING_SLOTS
+            ii += 1
+        assert done == n or (live and live[0] == done), "the chunk to consume was never issued"
+    assert ii == n

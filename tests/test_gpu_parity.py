@@ -23,8 +23,17 @@ def wrap(A, op):
     return A if op == "N" else (B.transpose(A) if op == "T" else B.adjoint(A))
 
 
-def battery(A, seed=0, ops=OPS, reps=2):
-    """A*x, A'*x, transpose(A)*x and 5-arg mul! (α=im|0.7, β=2im|-0.4) vs the oracle."""
+def battery(A, seed=0, ops=OPS, reps=2, variants=None):
+    """A*x, A'*x, transpose(A)*x and 5-arg mul! (α=im|0.7, β=2im|-0.4) vs the oracle, for the stream
+    (AUTO: TMA-staged kernels) and the GATHER (direct loads) plans."""
+    if variants is None and not isinstance(A, B.SymmetricBlockMatrix):
+        variants = (L.VARIANT_AUTO, L.VARIANT_GATHER)
+    if variants:
+        for v in variants:
+            A.device().set_variant(v)
+            battery(A, seed, ops, reps, variants=False)
+        A.device().set_variant(L.VARIANT_AUTO)
+        return
     dt = np.dtype(A.dtype)
     tol = TOL[dt]
     f64 = dt == np.float32

@@ -218,6 +218,41 @@ def test_slab_plans_partition_the_product(fixture, op):
     assert rel(y, ref) < 1e-13
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+def test_warp_stream_schedule_c3_shape(dtype):
+    """C3-shaped VBCRS: every block row goes to the warp-stream kernel; the chunk stream, its ring
+    placement and the work items are replayed by the interpreter (several items, ring wrap-around)."""
+    from bsm_b200 import generators as G
+    V = G.vbcrs_variable(seed=21, n=30000, dtype=dtype)
+    D = host_only(V)
+    OV = O.OVBCRS(V.blocks, V.rowptr, V.colindices, V.rowindices, V.size)
+    rng = np.random.default_rng(7)
+    tol = 1e-5 if dtype == np.float32 else 1e-13
+    for op in OPS:
+        st = D.plan_stats(op)
+        assert st["slices"]["stream_warp_kernel"] > 0 and st["slices"]["gather_gemv_kernel"] == 0
+        assert st["warp_items"] > 1 and D.launch_count(op) == 1
+        x = rng.standard_normal(30000).astype(dtype)
+        ref = O.mul_vbcrs(OV, x.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64), op)
+        assert rel(run_plan(V, D, op, x), ref) < tol
+    chunks = D.table(L.TAB_WCHUNK, 2)
+    assert chunks["lag"].max() >= 3           # several chunks in flight per warp
+
+
+def test_long_tform_segments_are_cut_into_column_ranges():
+    """C4-shaped transpose product: 1024-row blocks, output segments of 1024 columns are cut into
+    column sub-ranges for the CTA stream kernel (whole columns are contiguous in the arena)."""
+    from bsm_b200 import generators as G
+    A = G.blocksparse_large(seed=22, grid=3, bs=1024, density=0.5)
+    D = host_only(A)
+    st = D.plan_stats("T")
+    assert st["slices"]["sym_fused_tma_kernel"] > 3 and st["slices"]["gather_gemv_kernel"] == 0
+    OA = O.OBSM(A.blocks, A.rowindices, A.colindices, A.size)
+    x = np.random.default_rng(8).standard_normal(A.size[0]).astype(np.float32)
+    assert rel(run_plan(A, D, "T", x), O.mul_bsm(OA, x.astype(np.float64), "T")) < 1e-5
+    assert rel(run_plan(A, D, "N", x), O.mul_bsm(OA, x.astype(np.float64), "N")) < 1e-5
+
+
 def test_errors():
     b = [np.ones((2, 2))]
     with pytest.raises(L.BsmError):      # index out of range
