@@ -53,6 +53,11 @@ def workload_spec(name, scale):
         g = max(4, int(round(64 * np.sqrt(scale))))
         return dict(kind="BlockSparseMatrix", dtype="f32", n=g * 1024, grid=g,
                     desc=f"C4 BlockSparseMatrix Float32 1024^2 blocks 5% of {g}x{g} grid, transpose(A)*x")
+    if name == "c5":
+        n = max(6400, int(1_000_000 * scale) // 32 * 32)
+        return dict(kind="BlockSparseMatrix", dtype="f64", n=n, nblocks=max(1000, int(200_000 * scale)), nrhs=64,
+                    desc=f"C5 BlockSparseMatrix Float64 N={n}, {max(1000, int(200_000 * scale))} blocks 32x32, "
+                         f"Y = A*X with 64 right-hand sides (SpMM)")
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -74,6 +79,8 @@ def build_workload(name, scale, rank=0, world=1, threads=8):
         return G.vbcrs_variable(seed=3, n=spec["n"], threads=threads), "N", None, None
     if name == "c1":
         return G.blocksparse_uniform(seed=1, threads=threads), "N", None, None
+    if name == "c5":
+        return G.blocksparse_uniform(seed=5, n=spec["n"], nblocks=spec["nblocks"], threads=threads), "N", None, None
     return G.blocksparse_large(seed=4, grid=spec["grid"], threads=threads), "T", None, None
 
 
@@ -134,6 +141,7 @@ def cpu_sample(name, scale_hint, steps, warmup, min_seconds=8.0):
     from oracle import oracle_np as O
 
     threads = os.cpu_count() or 1
+    nrhs = 1
     if name == "c2":
         n = min(100_000, workload_spec(name, scale_hint)["n"])
         A = G.symmetric_nearfield(seed=2, n=n, threads=min(threads, 16))
@@ -147,10 +155,14 @@ def cpu_sample(name, scale_hint, steps, warmup, min_seconds=8.0):
     elif name == "c1":
         A = G.blocksparse_uniform(seed=1)
         sample, op = f"full C1 matrix, {threads} threads", "N"
+    elif name == "c5":
+        A = G.blocksparse_uniform(seed=5, n=100_000 // 32 * 32, nblocks=20_000)
+        sample, op = f"same generator at N={A.size[0]}, 20000 blocks, 64 right-hand sides as a column loop, {threads} threads", "N"
+        nrhs = 64
     else:
         A = G.blocksparse_large(seed=4, grid=16)
         sample, op = f"same generator on a 16x16 grid (13 blocks), {threads} threads", "T"
-    work = A.device(device=L.DEVICE_NONE).work(op)
+    work = A.device(device=L.DEVICE_NONE).work(op, nrhs=nrhs)
     OA = to_oracle(A)
     rng = np.random.default_rng(0)
     x = rng.standard_normal(A.size[1]).astype(A.dtype)
@@ -161,6 +173,9 @@ def cpu_sample(name, scale_hint, steps, warmup, min_seconds=8.0):
         run = lambda: O.c_mul_vbcrs(OA, x, op, threads=threads)
     else:
         run = lambda: O.c_mul_bsm(OA, x, op, threads=threads)
+    if nrhs > 1:      # LinearMaps applies a matrix right-hand side column by column
+        one = run
+        run = lambda: [one() for _ in range(nrhs)]
     for _ in range(max(1, min(warmup, 2))):
         run()
     times = []
@@ -202,7 +217,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
     ap.add_argument("--variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -238,7 +253,8 @@ def main():
     tdt = {"c128": torch.complex128, "f64": torch.float64, "f32": torch.float32}[spec["dtype"]]
     nin = A.size[1] if op == "N" else A.size[0]
     nout = A.size[0] if op == "N" else A.size[1]
-    work = D.work(op)
+    nrhs = spec.get("nrhs", 1)
+    work = D.work(op, nrhs=nrhs)
     if world > 1:
         # whole-job algorithmic bytes: every stored entry once (slabs duplicate boundary blocks, that is
         # overhead, not work) — computed from the structure on rank 0's formula for the full matrix
@@ -250,10 +266,15 @@ def main():
                 "index_table_bytes": 0.0}
 
     g = torch.Generator(device="cpu").manual_seed(1234)
-    x_host = torch.randn(nin, dtype=tdt, generator=g).pin_memory()
-    y_host = torch.empty(nout, dtype=tdt).pin_memory()
-    x_full = x_host.to(dev)
-    y_dev = torch.zeros(nout, dtype=tdt, device=dev)
+    if nrhs == 1:
+        x_host = torch.randn(nin, dtype=tdt, generator=g).pin_memory()
+        y_host = torch.empty(nout, dtype=tdt).pin_memory()
+        y_dev = torch.zeros(nout, dtype=tdt, device=dev)
+    else:   # column-major (nin x nrhs) / (nout x nrhs)
+        x_host = torch.randn((nrhs, nin), dtype=tdt, generator=g).pin_memory().t()
+        y_host = torch.empty((nrhs, nout), dtype=tdt).pin_memory().t()
+        y_dev = torch.zeros((nrhs, nout), dtype=tdt, device=dev).t()
+    x_full = x_host.to(dev) if nrhs == 1 else x_host.t().to(dev).t()
 
     if world > 1:
         x_local = x_full[own[0]:own[1]].clone()
@@ -304,12 +325,12 @@ def main():
         fin_ms.append(b)
     D.set_profiling(False)
     k_ms = float(np.mean(main_ms))
-    local_work = D.work(op)
+    local_work = D.work(op, nrhs=nrhs)
 
     # end to end through the host-pointer C-ABI call: pinned host x → H2D → multiply → D2H → host y
     e2e = None
     if world == 1:
-        xh, yh = x_host.numpy(), y_host.numpy()
+        xh, yh = (x_host.numpy(), y_host.numpy()) if nrhs == 1 else (x_host.t().numpy().T, y_host.t().numpy().T)
         for _ in range(2):
             D.mul(op, xh, yh)
         t0 = time.perf_counter()
@@ -353,6 +374,26 @@ def main():
     kernel_name = max(stats["bytes"], key=stats["bytes"].get)
     if kernel_name == "sym_fused_tma_kernel" and args.variant == 2:
         kernel_name = "sym_fused_kernel"
+    tensor = None
+    if nrhs >= 8 and stats["spmm"] and args.variant != 1:
+        kernel_name = "spmm_dmma_kernel"
+        # FP64 tensor-pipe denominator: cuBLAS DGEMM measured here (MEASURED_PEAKS.json holds no FP64 figure)
+        a64 = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+        b64 = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            torch.matmul(a64, b64)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        best = 1e9
+        for _ in range(5):
+            ev[0].record()
+            torch.matmul(a64, b64)
+            ev[1].record()
+            torch.cuda.synchronize()
+            best = min(best, ev[0].elapsed_time(ev[1]))
+        dgemm_tf = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
+        ach_tf = local_work["flops"] / (k_ms * 1e-3) / 1e12
+        tensor = {"bound": "tensor", "achieved": ach_tf, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": ach_tf / dgemm_tf,
+                  "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (best of 5)"}
     line = {
         "metric": METRIC, "value": work["bytes"] / (ms_step * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -369,9 +410,11 @@ def main():
                      "finalize_ms": float(np.mean(fin_ms)), "peak_source": peak_src,
                      "bytes_per_launch": local_work["bytes"]},
         "e2e": e2e,
-        "gpu_launches": int(args.steps * D.launch_count(op)),
+        "gpu_launches": int(args.steps * (D.launch_count(op) if nrhs == 1 or tensor is None else 1)),
         "clocks": clocks,
     }
+    if tensor is not None:
+        line["roofline_tensor"] = tensor
     if world == 1 and not args.no_cpu_baseline:
         gbs, cores, sample, sec, gflops = cpu_sample(args.workload, args.scale, 3, 1)
         line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample,

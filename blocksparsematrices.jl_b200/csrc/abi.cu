@@ -4,6 +4,7 @@
 // point needs a CUDA device and fails with BSM_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -13,6 +14,7 @@
 
 #include "kernels.cuh"
 #include "plan.h"
+#include "spmm.cuh"
 
 using namespace bsm;
 
@@ -60,10 +62,11 @@ struct DevPlan {
     DevBuf<int32_t> gather_rows;
     DevBuf<int64_t> gather_ptr, gather_pos;
     DevBuf<bsm_wchunk> wchunk;
-    DevBuf<int32_t> witem_ptr;
+    DevBuf<int32_t> witem_ptr, mitem_ptr;
     void release() {
         wchunk.release();
         witem_ptr.release();
+        mitem_ptr.release();
         contrib.release();
         contrib_toff.release();
         slices.release();
@@ -215,6 +218,7 @@ int upload_tables(bsm_matrix *A) {
         if (int rc = A->plan[p].gather_pos.upload(H.plan[p].gather_pos)) return rc;
         if (int rc = A->plan[p].wchunk.upload(H.plan[p].wchunk)) return rc;
         if (int rc = A->plan[p].witem_ptr.upload(H.plan[p].witem_ptr)) return rc;
+        if (int rc = A->plan[p].mitem_ptr.upload(H.plan[p].mitem_ptr)) return rc;
     }
     return 0;
 }
@@ -316,6 +320,65 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
     if (HP.scratch_elems > 0)
         CUDA_TRY(cudaMallocAsync((void **)&scratch, (size_t)HP.scratch_elems * sizeof(T), st));
     constexpr int VMAX = 16 / (int)sizeof(T);
+    if constexpr (sizeof(T) == 8) {
+        // many right-hand sides: one pass over A on the FP64 tensor cores instead of nrhs SpMV passes
+        if (nrhs >= kSpmmMinRhs && HP.spmm_ok && A->variant != BSM_VARIANT_GATHER && p >= 2) {
+            static bool spmm_attr = false;
+            if (!spmm_attr) {
+                CUDA_TRY(cudaFuncSetAttribute(spmm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)std::max(spmm_smem_bytes(true), spmm_smem_bytes(false))));
+                spmm_attr = true;
+            }
+            SpmmArgs m;
+            m.arena = (const double *)A->arena;
+            m.contrib = DP.contrib.p;
+            m.slices = DP.slices.p;
+            m.item_ptr = DP.mitem_ptr.p;
+            m.set_start = A->set_start.p;
+            m.set_pool_off = A->set_pool_off.p;
+            m.pool = A->pool.p;
+            m.x = (const double *)x;
+            m.y = (double *)y;
+            m.ldx = ldx;
+            m.ldy = ldy;
+            std::memcpy(&m.alpha, alpha, 8);
+            m.beta = 0.0;
+            if (!beta_is_false) std::memcpy(&m.beta, beta, 8);
+            m.nrhs = (int32_t)nrhs;
+            m.beta_false = beta_is_false ? 1 : 0;
+            m.abytes = HP.spmm_small ? kMABytesSmall : kMABytesBig;
+            m.nstages = spmm_stages(HP.spmm_small);
+            const bool prof = A->profiling;
+            if (prof) CUDA_TRY(cudaEventRecord(A->ev[0], st));
+            dim3 grid((unsigned)(HP.mitem_ptr.size() - 1), (unsigned)((nrhs + kMRhs - 1) / kMRhs));
+            spmm_dmma_kernel<<<grid, kMThreads, spmm_smem_bytes(HP.spmm_small), st>>>(m);
+            CUDA_TRY(cudaGetLastError());
+            if (prof) CUDA_TRY(cudaEventRecord(A->ev[1], st));
+            const int64_t ng = (int64_t)HP.gather_rows.size();
+            if (ng > 0) {
+                // rows no block touches: y = beta*y (there are no partial sums on this path)
+                FinalizeArgs<T> f;
+                f.rows = DP.gather_rows.p;
+                f.ptr = DP.gather_ptr.p;
+                f.pos = DP.gather_pos.p;
+                f.scratch = nullptr;
+                std::memcpy(&f.alpha, alpha, sizeof(T));
+                std::memcpy(&f.beta, &m.beta, sizeof(T));
+                f.n = ng;
+                f.ldy = ldy;
+                f.beta_false = m.beta_false;
+                f.y = y;
+                for (int64_t jb = 0; jb < nrhs; jb += 65535) {   // grid.y limit
+                    f.y = y + jb * ldy;
+                    dim3 fg((unsigned)((ng + 255) / 256), (unsigned)std::min<int64_t>(65535, nrhs - jb));
+                    gather_finalize_kernel<T><<<fg, 256, 0, st>>>(f);
+                }
+                CUDA_TRY(cudaGetLastError());
+            }
+            if (prof) CUDA_TRY(cudaEventRecord(A->ev[2], st));
+            return 0;
+        }
+    }
     for (int64_t j = 0; j < nrhs; ++j) {
         MulArgs<T> a;
         a.arena = (const T *)A->arena;
@@ -338,6 +401,7 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
         a.beta_false = beta_is_false ? 1 : 0;
         a.conj = (op == BSM_OP_C && sizeof(T) == 16) ? 1 : 0;
         const bool prof = A->profiling && nrhs == 1;
+        if (A->profiling && nrhs > 1 && j == 0) CUDA_TRY(cudaEventRecord(A->ev[0], st));
         if (prof) CUDA_TRY(cudaEventRecord(A->ev[0], st));
         if (nfused > 0) {
             if (use_tma)
@@ -386,11 +450,16 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             f.alpha = a.alpha;
             f.beta = a.beta;
             f.n = ng;
+            f.ldy = 0;
             f.beta_false = a.beta_false;
             gather_finalize_kernel<T><<<(unsigned)((ng + 255) / 256), 256, 0, st>>>(f);
             CUDA_TRY(cudaGetLastError());
         }
         if (prof) CUDA_TRY(cudaEventRecord(A->ev[2], st));
+        if (A->profiling && nrhs > 1 && j == nrhs - 1) {   // column loop: one bracket around all columns
+            CUDA_TRY(cudaEventRecord(A->ev[1], st));
+            CUDA_TRY(cudaEventRecord(A->ev[2], st));
+        }
     }
     if (scratch) CUDA_TRY(cudaFreeAsync(scratch, st));
     return 0;
@@ -786,12 +855,12 @@ int bsm_work(bsm_handle h, int op, int64_t nrhs, int beta_used, double *bytes, d
     return 0;
 }
 
-int bsm_plan_stats(bsm_handle h, int op, int64_t out[10]) {
+int bsm_plan_stats(bsm_handle h, int op, int64_t out[12]) {
     if (int rc = check_handle(h)) return rc;
     if (op < BSM_OP_N || op > BSM_OP_C || !out) return fail(BSM_ERR_ARG, "bad op or null output");
     const HostPlan &P = h->H.plan[plan_index(h, op)];
     const int64_t s = dtype_size(h->H.dtype);
-    for (int i = 0; i < 10; ++i) out[i] = 0;
+    for (int i = 0; i < 12; ++i) out[i] = 0;
     for (size_t i = 0; i < P.slices.size(); ++i) {
         const bsm_slice &sl = P.slices[i];
         const int cls = (sl.flags & kSliceFused) ? 0 : (sl.flags & kSliceWarp) ? 1 : 2;
@@ -806,6 +875,7 @@ int bsm_plan_stats(bsm_handle h, int op, int64_t out[10]) {
     out[7] = (int64_t)P.wchunk.size();
     out[8] = P.scratch_elems;
     out[9] = (int64_t)P.gather_rows.size();
+    out[10] = P.spmm_ok ? (int64_t)P.mitem_ptr.size() - 1 : 0;
     return 0;
 }
 

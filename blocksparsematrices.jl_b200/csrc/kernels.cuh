@@ -1031,6 +1031,7 @@ struct FinalizeArgs {
     T *y;
     T alpha, beta;
     int64_t n;
+    int64_t ldy;
     int32_t beta_false;
 };
 
@@ -1040,15 +1041,16 @@ __global__ void __launch_bounds__(256) gather_finalize_kernel(const FinalizeArgs
     if (i >= a.n) return;
     const int32_t rr = a.rows[i];
     const int32_t row = rr & 0x7fffffff;
+    T *y = a.y + (int64_t)blockIdx.y * a.ldy;   // blockIdx.y: right-hand side (multi-RHS path, no partial sums)
     T s = El<T>::zero();
     for (int64_t k = a.ptr[i]; k < a.ptr[i + 1]; ++k) s = El<T>::add(s, a.scratch[a.pos[k]]);
     T v = El<T>::mul(a.alpha, s);
     if (rr < 0) {
-        v = El<T>::add(v, a.y[row]);  // a direct slice already wrote alpha*acc + beta*y here
+        v = El<T>::add(v, y[row]);  // a direct slice already wrote alpha*acc + beta*y here
     } else if (!a.beta_false) {
-        v = El<T>::add(v, El<T>::mul(a.beta, a.y[row]));
+        v = El<T>::add(v, El<T>::mul(a.beta, y[row]));
     }
-    a.y[row] = v;
+    y[row] = v;
 }
 
 }  // namespace bsm

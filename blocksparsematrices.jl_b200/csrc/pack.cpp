@@ -474,6 +474,31 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
             }
         }
     }
+    // 8. multi-RHS work items: the SpMM kernel walks slices/contributions itself (its producer warp runs
+    //    ahead of the tensor-core consumers), so an item is just a range of slices
+    P.spmm_ok = P.n_warp_slices > 0 && P.n_warp_slices == (int64_t)P.slices.size() && P.gather_pos.empty();
+    for (const auto &sl : P.slices)
+        if (!(sl.flags & kSliceDirect)) P.spmm_ok = false;
+    if (P.spmm_ok) {
+        int64_t total = 0;
+        P.spmm_small = true;
+        for (const auto &c : P.contrib) {
+            total += (int64_t)c.m * c.n * s;
+            if (c.m > 32 || ((c.form & kFormT) && c.n > 32)) P.spmm_small = false;
+        }
+        const int64_t target = std::max<int64_t>(128 << 10, total / (148 * 2 * 8));
+        P.mitem_ptr.push_back(0);
+        int64_t acc = 0;
+        for (size_t i = 0; i < P.slices.size(); ++i) {
+            for (int32_t c = P.slices[i].c_begin; c < P.slices[i].c_end; ++c)
+                acc += (int64_t)P.contrib[c].m * P.contrib[c].n * s;
+            if (acc >= target) {
+                P.mitem_ptr.push_back((int32_t)(i + 1));
+                acc = 0;
+            }
+        }
+        if (P.mitem_ptr.back() != (int32_t)P.slices.size()) P.mitem_ptr.push_back((int32_t)P.slices.size());
+    }
     return std::string();
 }
 

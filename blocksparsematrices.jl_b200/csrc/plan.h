@@ -97,6 +97,11 @@ struct HostPlan {
     int64_t n_warp_slices = 0;          // follow the fused slices; the rest go to gather_gemv_kernel
     std::vector<bsm_wchunk> wchunk;     // chunk stream of the warp slices, in slice order
     std::vector<int32_t> witem_ptr;     // warp work items: chunk ranges cut at segment boundaries
+    // multi-RHS (SpMM) path: usable when every slice is a direct warp-class slice (short segments that
+    // own their rows); CTA work items = ranges of those slices, balanced by bytes
+    bool spmm_ok = false;
+    bool spmm_small = false;            // no block has more than 32 rows or columns (4-stage ring)
+    std::vector<int32_t> mitem_ptr;
     std::vector<int32_t> gather_rows;
     std::vector<int64_t> gather_ptr;
     std::vector<int64_t> gather_pos;

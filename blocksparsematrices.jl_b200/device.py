@@ -163,12 +163,12 @@ class DeviceMatrix:
 
     def plan_stats(self, op="N") -> dict:
         """Work split of the plan used for `op` between the three multiply kernels."""
-        out = np.zeros(10, np.int64)
+        out = np.zeros(12, np.int64)
         L.check(L.lib().bsm_plan_stats(self._h, _OPS[op], _i64p(out)))
         names = ("sym_fused_tma_kernel", "stream_warp_kernel", "gather_gemv_kernel")
         return {"slices": dict(zip(names, out[0:3].tolist())), "bytes": dict(zip(names, out[3:6].tolist())),
                 "warp_items": int(out[6]), "warp_chunks": int(out[7]), "scratch_elems": int(out[8]),
-                "finalized_rows": int(out[9])}
+                "finalized_rows": int(out[9]), "spmm": int(out[10])}
 
     def set_profiling(self, on: bool):
         L.check(L.lib().bsm_set_profiling(self._h, int(on)))

@@ -151,8 +151,10 @@ int bsm_launch_count(bsm_handle h, int op);
 /* Work split of the plan bsm_mul uses for `op` with the current variant. out[0..2] = slices handled by
  * the CTA-stream kernel (sym_fused_tma_kernel), the warp-stream kernel (stream_warp_kernel) and the
  * gather kernel (gather_gemv_kernel); out[3..5] = block bytes each of them streams; out[6] = warp work
- * items; out[7] = warp-stream chunks; out[8] = scratch elements; out[9] = rows finalised by the gather pass. */
-int bsm_plan_stats(bsm_handle h, int op, int64_t out[10]);
+ * items; out[7] = warp-stream chunks; out[8] = scratch elements; out[9] = rows finalised by the gather pass;
+ * out[10] = CTA work items of the multi-RHS (SpMM) kernel, 0 if the plan is not eligible for it (then
+ * nrhs > 1 loops over the columns); out[11] reserved. */
+int bsm_plan_stats(bsm_handle h, int op, int64_t out[12]);
 
 /* ---- table export (bit-exact packing checks) ---------------------------------------------- */
 typedef enum {

@@ -213,3 +213,50 @@ def test_real_matrix_complex_x_promotes():
     y = A * x
     ref = oracle_mul(A, np.ascontiguousarray(x.real), "N") + 1j * oracle_mul(A, np.ascontiguousarray(x.imag), "N")
     assert rel2(y, ref) < 1e-12
+
+
+# ---- multi-RHS SpMM (C5): FP64 tensor-core kernel vs the oracle applied column by column ------------------
+def spmm_check(A, nrhs, ops=OPS, seed=3):
+    import torch
+    rng = np.random.default_rng(seed)
+    D = A.device()
+    for op in ops:
+        assert D.plan_stats(op)["spmm"], "plan is not eligible for the SpMM kernel"
+        nin = A.size[1] if op == "N" else A.size[0]
+        nout = A.size[0] if op == "N" else A.size[1]
+        X = np.asfortranarray(rng.standard_normal((nin, nrhs)))
+        Y0 = np.asfortranarray(rng.standard_normal((nout, nrhs)))
+        ref = np.stack([oracle_mul(A, np.ascontiguousarray(X[:, j]), op) for j in range(nrhs)], axis=1)
+        Y = wrap(A, op) * X                                        # host pointers (bsm_mul_host)
+        assert Y.shape == (nout, nrhs) and rel2(Y, ref) < 1e-12, (op, nrhs)
+        ref5 = np.stack([oracle_mul(A, np.ascontiguousarray(X[:, j]), op, 0.7, -0.4, False, Y0[:, j].copy())
+                         for j in range(nrhs)], axis=1)
+        Y5 = B.mul_(Y0.copy(order="F"), wrap(A, op), X, 0.7, -0.4)
+        assert rel2(Y5, ref5) < 1e-12, (op, nrhs, "5-arg")
+        # device pointers with a padded leading dimension
+        Xd = torch.zeros((nrhs, nin + 3), dtype=torch.float64, device="cuda").t()[:nin]
+        Xd.copy_(torch.from_numpy(X))
+        Yd = D.mul(op, Xd)
+        assert rel2(Yd.cpu().numpy(), ref) < 1e-12
+        # the column loop over the SpMV kernels (what LinearMaps does) gives the same answer
+        D.set_variant(L.VARIANT_GATHER)
+        assert rel2(D.mul(op, X), ref) < 1e-12
+        D.set_variant(L.VARIANT_AUTO)
+
+
+@pytest.mark.parametrize("nrhs", [8, 13, 64, 70])
+def test_c5_shape_spmm(nrhs):
+    A = G.blocksparse_uniform(seed=31, n=6400, nblocks=1500, bs=32)
+    spmm_check(A, nrhs)
+
+
+def test_spmm_variable_blocks_and_permuted_indices():
+    spmm_check(G.vbcrs_variable(seed=32, n=20000), 24)                       # odd sizes: 8-byte copy paths
+    spmm_check(G.blocksparse_uniform(seed=33, n=3200, nblocks=400, bs=32, permuted=True), 16)   # index pool
+    spmm_check(G.blocksparse_uniform(seed=34, n=2560, nblocks=300, bs=64), 32)                 # 64-row blocks
+
+
+def test_spmm_deterministic():
+    A = G.blocksparse_uniform(seed=35, n=6400, nblocks=1500, bs=32)
+    X = np.asfortranarray(np.random.default_rng(0).standard_normal((6400, 64)))
+    assert np.array_equal(A * X, A * X)
