@@ -73,8 +73,6 @@ def build_workload(name, scale, rank=0, world=1, threads=8):
         A = G.symmetric_nearfield(seed=2, n=spec["n"], threads=threads, leaves=(int(cuts[rank]), int(cuts[rank + 1])))
         rb = S.bounds[cuts]
         return A, "N", (int(rb[rank]), int(rb[rank + 1])), rb
-    if world > 1:
-        raise SystemExit("multi-GPU slabs are implemented for the c2 workload")
     if name == "c3":
         return G.vbcrs_variable(seed=3, n=spec["n"], threads=threads), "N", None, None
     if name == "c1":
@@ -247,7 +245,19 @@ def main():
     A, op, own, rb = build_workload(args.workload, args.scale, rank, world, threads=min(host_threads, 32))
     t_gen = time.time() - t0
     t0 = time.time()
-    D = B.DeviceMatrix(A, device=local, variant=args.variant, own_rows=own, own_cols=own)
+    full_work = None
+    if world > 1:
+        # one process per GPU: nnz-balanced block-row slabs, libbsm_b200's own NCCL communicator
+        from bsm_b200.dist import Comm, SlabMatrix
+        comm = Comm.from_torch(local)
+        if rb is None:        # generic partition of the full host matrix (every rank generated it)
+            full_work = A.device(device=L.DEVICE_NONE).work(op, nrhs=spec.get("nrhs", 1))
+            SM = SlabMatrix(A, comm, ops=(op,), variant=args.variant)
+        else:                 # c2: every rank generated only its slab's blocks
+            SM = SlabMatrix(A, comm, cuts=rb, variant=args.variant)
+        D, own, rb = SM.local, SM.own, SM.cuts
+    else:
+        D = B.DeviceMatrix(A, device=local, variant=args.variant)
     torch.cuda.synchronize()
     t_pack = time.time() - t0
     tdt = {"c128": torch.complex128, "f64": torch.float64, "f32": torch.float32}[spec["dtype"]]
@@ -255,7 +265,9 @@ def main():
     nout = A.size[0] if op == "N" else A.size[1]
     nrhs = spec.get("nrhs", 1)
     work = D.work(op, nrhs=nrhs)
-    if world > 1:
+    if world > 1 and full_work is not None:
+        work = full_work
+    elif world > 1:
         # whole-job algorithmic bytes: every stored entry once (slabs duplicate boundary blocks, that is
         # overhead, not work) — computed from the structure on rank 0's formula for the full matrix
         from bsm_b200 import generators as G
@@ -277,14 +289,8 @@ def main():
     x_full = x_host.to(dev) if nrhs == 1 else x_host.t().to(dev).t()
 
     if world > 1:
-        x_local = x_full[own[0]:own[1]].clone()
-        xr = torch.view_as_real(x_full) if tdt.is_complex else x_full
-        outs = [xr[int(rb[r]):int(rb[r + 1])] for r in range(world)]
-        x_local_r = torch.view_as_real(x_local) if tdt.is_complex else x_local
-
         def step():
-            dist.all_gather(outs, x_local_r)      # replicate x over NVLink (uneven slabs → grouped broadcasts)
-            D.mul(op, x_full, y_dev)
+            SM.mul(op, x_full, y_dev)   # bsm_mul_dist: NCCL all-gather of the x slabs (in place), then the slab multiply
     else:
         def step():
             D.mul(op, x_full, y_dev)
@@ -342,22 +348,36 @@ def main():
                "d2h_bytes_per_step": int(y_host.numel() * y_host.element_size())}
     else:
         # N > 1: each rank copies its x slice in and its y slice out every step
-        xs_h = x_host[own[0]:own[1]].clone().pin_memory()
-        ys_h = torch.empty(own[1] - own[0], dtype=tdt).pin_memory()
+        rows = own[1] - own[0]
+        if nrhs == 1:
+            xs_h = x_host[own[0]:own[1]].clone().pin_memory()
+            ys_h = torch.empty(rows, dtype=tdt).pin_memory()
+        else:   # slab rows of all columns: contiguous pinned buffers, strided placement done on the device
+            xs_h = x_host[own[0]:own[1]].t().contiguous().pin_memory()
+            ys_h = torch.empty((nrhs, rows), dtype=tdt).pin_memory()
+            xs_d, ys_d = torch.empty_like(xs_h, device=dev), torch.empty_like(ys_h, device=dev)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            x_local.copy_(xs_h, non_blocking=True)
+            if nrhs == 1:
+                x_full[own[0]:own[1]].copy_(xs_h, non_blocking=True)
+            else:
+                xs_d.copy_(xs_h, non_blocking=True)
+                x_full[own[0]:own[1]].copy_(xs_d.t())
             step()
-            ys_h.copy_(y_dev[own[0]:own[1]], non_blocking=True)
+            if nrhs == 1:
+                ys_h.copy_(y_dev[own[0]:own[1]], non_blocking=True)
+            else:
+                ys_d.copy_(y_dev[own[0]:own[1]].t())
+                ys_h.copy_(ys_d, non_blocking=True)
             torch.cuda.synchronize()
         barrier()
         t = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
         e2e = {"value": work["bytes"] / e2e_s / 1e9, "unit": "GB/s", "ms_per_step": e2e_s * 1e3,
-               "h2d_bytes_per_step": int(nin * x_host.element_size()),
-               "d2h_bytes_per_step": int(nout * y_host.element_size())}
+               "h2d_bytes_per_step": int(nin * nrhs * x_host.element_size()),
+               "d2h_bytes_per_step": int(nout * nrhs * y_host.element_size())}
 
     if rank != 0:
         if world > 1:

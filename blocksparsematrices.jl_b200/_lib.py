@@ -65,6 +65,14 @@ SIGNATURES = [
     ("bsm_plan_stats", c_int, [c_void_p, c_int, _P64]),
     ("bsm_table_count", c_int64, [c_void_p, c_int, c_int]),
     ("bsm_table_copy", c_int, [c_void_p, c_int, c_int, c_void_p, c_int64]),
+    ("bsm_dist_unique_id", c_int, [c_void_p]),
+    ("bsm_dist_init", c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),
+    ("bsm_dist_destroy", c_int, [c_void_p]),
+    ("bsm_dist_info", c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    ("bsm_dist_allgather_rows", c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, _P64, c_void_p]),
+    ("bsm_dist_allreduce_max_f64", c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    ("bsm_mul_dist", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p,
+                             c_int64, c_int64, _P64, c_void_p]),
     ("bsm_device_count", c_int, [POINTER(c_int)]),
     ("bsm_malloc", c_int, [c_int, c_size_t, POINTER(c_void_p)]),
     ("bsm_free", c_int, [c_int, c_void_p]),

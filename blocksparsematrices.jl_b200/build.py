@@ -13,7 +13,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libbsm_b200.so"
-SOURCES = ["abi.cu", "pack.cpp"]
+SOURCES = ["abi.cu", "dist.cu", "pack.cpp"]
 DEPS = ["kernels.cuh", "spmm.cuh", "plan.h", "../../include/bsm_b200.h"]
 
 NVCC_FLAGS = [
@@ -22,6 +22,7 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
     "-shared",
+    "-ldl",
 ]
 
 

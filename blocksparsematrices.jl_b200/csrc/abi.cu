@@ -27,6 +27,12 @@ int fail(int code, const std::string &msg) {
     return code;
 }
 
+}  // namespace
+
+void bsm_set_error(const std::string &msg) { g_err = msg; }   // used by dist.cu
+
+namespace {
+
 #define CUDA_TRY(expr)                                                                        \
     do {                                                                                      \
         cudaError_t e__ = (expr);                                                             \

@@ -1,0 +1,120 @@
+"""Single-box multi-GPU operator: block-row slabs + NCCL all-gather of x, through the C ABI
+(bsm_dist_* / bsm_mul_dist in include/bsm_b200.h). One process per GPU (torchrun); torch.distributed is
+used only for the rendezvous (shipping the 128-byte NCCL id), the data path is libbsm_b200's own
+communicator. No CPU fallback."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, byref, c_int, c_int64, c_void_p
+
+import numpy as np
+
+from . import _lib as L
+from .device import DeviceMatrix, _DT, _OPS, _torch_dtype
+from .partition import extract_slab, slab_cuts
+
+
+class Comm:
+    """NCCL communicator owned by libbsm_b200 (bsm_dist_init)."""
+
+    def __init__(self, id_bytes: bytes, nranks: int, rank: int, device: int):
+        self.nranks, self.rank, self.device = nranks, rank, device
+        h = c_void_p()
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(id_bytes)
+        L.check(L.lib().bsm_dist_init(buf, nranks, rank, device, byref(h)))
+        self._h = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (ctypes.c_ubyte * 128)()
+        L.check(L.lib().bsm_dist_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_torch(cls, device: int):
+        """Rendezvous over an initialised torch.distributed process group (any backend)."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(box[0], world, rank, device)
+
+    def nccl_version(self) -> int:
+        v = c_int(0)
+        L.check(L.lib().bsm_dist_info(self._h, None, None, byref(v)))
+        return int(v.value)
+
+    def allgather_rows(self, x, cuts, stream=None):
+        """In-place all-gather of the row slabs of a column-major CUDA tensor (vector or rows x nrhs)."""
+        import torch
+        dt = _DT[np.dtype({torch.float32: np.float32, torch.float64: np.float64,
+                           torch.complex128: np.complex128}[x.dtype])]
+        nrhs = 1 if x.dim() == 1 else x.shape[1]
+        ldx = x.shape[0] if x.dim() == 1 else x.stride(1)
+        if x.dim() == 2 and x.stride(0) != 1:
+            raise ValueError("x must be column-major (stride(0) == 1)")
+        c = np.ascontiguousarray(cuts, np.int64)
+        st = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
+        L.check(L.lib().bsm_dist_allgather_rows(self._h, dt, c_void_p(x.data_ptr()), ldx, nrhs,
+                                                c.ctypes.data_as(POINTER(c_int64)), c_void_p(st)))
+
+    def allreduce_max(self, t, stream=None):
+        import torch
+        assert t.dtype == torch.float64 and t.is_cuda
+        st = torch.cuda.current_stream(t.device).cuda_stream if stream is None else stream
+        L.check(L.lib().bsm_dist_allreduce_max_f64(self._h, c_void_p(t.data_ptr()), t.numel(), c_void_p(st)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.lib().bsm_dist_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SlabMatrix:
+    """Rank-local part of a block matrix cut into nnz-balanced block-row slabs.
+
+    SlabMatrix(A, comm)                 A: the full host matrix (every rank holds it; blocks are shared,
+                                        only this rank's slab is packed into HBM)
+    SlabMatrix(S, comm, cuts=cuts)      S: a host container that already holds only this rank's blocks
+    y = op(A) x: x is a full-length CUDA tensor of which this rank owns rows in_cuts[rank]:in_cuts[rank+1];
+    mul() all-gathers it in place and writes y[out_cuts[rank]:out_cuts[rank+1]].
+    """
+
+    def __init__(self, A, comm: Comm, cuts=None, ops=("N",), variant=L.VARIANT_AUTO):
+        self.comm = comm
+        self.size = A.size
+        if cuts is None:
+            if A.size[0] != A.size[1] and len(ops) > 1:
+                raise ValueError("one set of cuts serves rows and columns only for square matrices")
+            cuts = slab_cuts(A, comm.nranks, "N" if "N" in ops else "T")
+            lo, hi = int(cuts[comm.rank]), int(cuts[comm.rank + 1])
+            A = extract_slab(A, lo, hi, ops)
+        self.cuts = np.ascontiguousarray(cuts, np.int64)
+        lo, hi = int(self.cuts[comm.rank]), int(self.cuts[comm.rank + 1])
+        self.own = (lo, hi)
+        self.local = DeviceMatrix(A, device=comm.device, variant=variant, own_rows=(lo, hi), own_cols=(lo, hi))
+        self.dtype = self.local.dtype
+
+    def mul(self, op, x, y, alpha=True, beta=False, stream=None):
+        import torch
+        D = self.local
+        beta_false = isinstance(beta, (bool, np.bool_)) and not beta
+        a = np.array([alpha], dtype=D.dtype)
+        b = np.array([0 if beta_false else beta], dtype=D.dtype)
+        if x.dtype != _torch_dtype(D.dtype) or y.dtype != x.dtype or not x.is_cuda:
+            raise TypeError("x and y must be CUDA tensors of the operator's dtype")
+        nrhs = 1 if x.dim() == 1 else x.shape[1]
+        ldx = x.shape[0] if x.dim() == 1 else x.stride(1)
+        ldy = y.shape[0] if y.dim() == 1 else y.stride(1)
+        st = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
+        L.check(L.lib().bsm_mul_dist(self.comm._h, D._h, _OPS[op], a.ctypes.data_as(c_void_p),
+                                     b.ctypes.data_as(c_void_p), int(beta_false), c_void_p(x.data_ptr()), ldx,
+                                     c_void_p(y.data_ptr()), ldy, nrhs,
+                                     self.cuts.ctypes.data_as(POINTER(c_int64)), c_void_p(st)))
+        return y

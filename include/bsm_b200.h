@@ -233,6 +233,29 @@ typedef struct {
 int64_t bsm_table_count(bsm_handle h, int table, int plan); /* number of elements/records, <0 on error */
 int bsm_table_copy(bsm_handle h, int table, int plan, void *dst, int64_t dst_bytes);
 
+/* ---- single-box multi-GPU: block-row slabs + NCCL all-gather of x ------------------
+ * One process per GPU. Rank r builds its handle from the blocks of its slab with
+ * bsm_options.own_row_* / own_col_* = its output range, keeps a FULL-length x on its device and owns
+ * rows [cuts[r], cuts[r+1]) of it. bsm_mul_dist first replicates x (one NCCL group of in-place broadcasts
+ * per rank and right-hand side, directly on the column-major array — slabs are uneven), then multiplies;
+ * each rank writes only its own slice of y. NCCL is bound at run time (dlopen "libnccl.so.2"). The
+ * reference has no counterpart (single process). */
+typedef struct bsm_comm_s *bsm_comm;
+#define BSM_DIST_ID_BYTES 128
+int bsm_dist_unique_id(void *id128);       /* rank 0: ncclGetUniqueId; ship the 128 bytes to every rank */
+int bsm_dist_init(const void *id128, int nranks, int rank, int device, bsm_comm *out);
+int bsm_dist_destroy(bsm_comm c);
+int bsm_dist_info(bsm_comm c, int *nranks, int *rank, int *nccl_version);
+/* In-place all-gather of the row slabs of a column-major (rows x nrhs, leading dimension ldx) DEVICE
+ * array: on return every rank holds all rows. cuts has nranks+1 entries (0-based, non-decreasing). */
+int bsm_dist_allgather_rows(bsm_comm c, int dtype, void *x_dev, int64_t ldx, int64_t nrhs, const int64_t *cuts,
+                            void *stream);
+int bsm_dist_allreduce_max_f64(bsm_comm c, double *dev_values, int64_t count, void *stream);
+/* all-gather of x over in_cuts, then bsm_mul on this rank's slab. */
+int bsm_mul_dist(bsm_comm c, bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
+                 void *x_dev, int64_t ldx, void *y_dev, int64_t ldy, int64_t nrhs, const int64_t *in_cuts,
+                 void *stream);
+
 /* ---- device memory helpers for callers without a CUDA array package ------------------------ */
 int bsm_device_count(int *count);
 int bsm_malloc(int device, size_t bytes, void **dev_ptr);

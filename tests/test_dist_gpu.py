@@ -1,0 +1,89 @@
+"""Two-GPU parity of the slab path through the C ABI (bsm_dist_init / bsm_mul_dist): NCCL all-gather of the
+x slabs + slab multiply on every rank, against the oracle. Skipped on boxes with fewer than two GPUs."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)      # rendezvous only
+    import bsm_b200 as B
+    from bsm_b200 import generators as G
+    from bsm_b200.dist import Comm, SlabMatrix
+    from helpers import oracle_mul, rel2
+
+    comm = Comm.from_torch(rank)
+    errs = {}
+    cases = [("sbm", G.symmetric_nearfield(seed=51, n=30000, k_near=4), 1, ("N", "C")),
+             ("vbcrs", G.vbcrs_variable(seed=52, n=60000), 1, ("N", "T")),
+             ("spmm", G.blocksparse_uniform(seed=53, n=12800, nblocks=3000, bs=32), 16, ("N",))]
+    for name, A, nrhs, ops in cases:
+        SM = SlabMatrix(A, comm, ops=ops)
+        lo, hi = SM.own
+        n = A.size[0]
+        rng = np.random.default_rng(7)
+        shape = (n,) if nrhs == 1 else (n, nrhs)
+        xt = rng.standard_normal(shape)
+        if np.dtype(A.dtype).kind == "c":
+            xt = xt + 1j * rng.standard_normal(shape)
+        xt = np.asfortranarray(xt.astype(A.dtype))
+        for op in ops:
+            xh = np.full(shape, np.nan, A.dtype, order="F")       # only the own slab is valid before the gather
+            xh[lo:hi] = xt[lo:hi]
+            x = torch.from_numpy(xh.T.copy()).cuda().T if nrhs > 1 else torch.from_numpy(xh).cuda()
+            y = torch.zeros_like(x)
+            SM.mul(op, x, y)
+            torch.cuda.synchronize()
+            assert np.array_equal(x.cpu().numpy(), xt), "all-gather did not replicate x"
+            got = y.cpu().numpy()[lo:hi]
+            if nrhs == 1:
+                ref = oracle_mul(A, xt, op)[lo:hi]
+            else:
+                ref = np.stack([oracle_mul(A, np.ascontiguousarray(xt[:, j]), op) for j in range(nrhs)], axis=1)[lo:hi]
+            errs[(name, op)] = rel2(got, ref)
+            assert not np.any(y.cpu().numpy()[:lo] != 0) and not np.any(y.cpu().numpy()[hi:] != 0)
+    out = [None] * world
+    dist.all_gather_object(out, errs)
+    if rank == 0:
+        q.put((out, comm.nccl_version()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
+def test_two_gpu_slabs_match_oracle():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out, ver = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ver >= 21800
+    for errs in out:
+        assert all(e < 1e-12 for e in errs.values()), errs
