@@ -18,7 +18,7 @@ DEVICE_NONE = -2
 
 (TAB_ARENA, TAB_BLOCK_OFF, TAB_BLOCK_M, TAB_BLOCK_N, TAB_SET_LEN, TAB_SET_START, TAB_SET_POOL_OFF,
  TAB_POOL, TAB_CONTRIB, TAB_SLICE, TAB_GATHER_ROWS, TAB_GATHER_PTR, TAB_GATHER_POS, TAB_GROUP_PTR,
- TAB_GROUP_SET, TAB_CONTRIB_TOFF, TAB_WCHUNK, TAB_WITEM_PTR) = range(18)
+ TAB_GROUP_SET, TAB_CONTRIB_TOFF, TAB_WCHUNK, TAB_WITEM_PTR, TAB_COLOR_PTR) = range(19)
 
 
 class Options(ctypes.Structure):

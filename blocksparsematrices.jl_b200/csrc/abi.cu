@@ -91,7 +91,7 @@ struct bsm_matrix {
     void *arena = nullptr;
     DevBuf<int32_t> set_len, set_start, pool;
     DevBuf<int64_t> set_pool_off;
-    DevPlan plan[4];
+    DevPlan plan[6];
     // host-pointer path
     std::mutex host_mu;
     void *hx = nullptr, *hy = nullptr;
@@ -214,8 +214,9 @@ int upload_tables(bsm_matrix *A) {
     if (int rc = A->set_start.upload(H.sets.start)) return rc;
     if (int rc = A->set_pool_off.upload(H.sets.pool_off)) return rc;
     if (int rc = A->pool.upload(H.sets.pool)) return rc;
-    for (int p = 0; p < 4; ++p) {
-        if (p >= 2 && !H.has_fused) break;
+    for (int p = 0; p < 6; ++p) {
+        if (p >= 2 && p < 4 && !H.has_fused) continue;
+        if (p >= 4 && !H.plan[p].color_ok) continue;
         if (int rc = A->plan[p].contrib.upload(H.plan[p].contrib)) return rc;
         if (int rc = A->plan[p].contrib_toff.upload(H.plan[p].contrib_toff)) return rc;
         if (int rc = A->plan[p].slices.upload(H.plan[p].slices)) return rc;
@@ -255,6 +256,9 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
         if (err.empty()) err = build_plan(H, ir[2], H.nrows, H.ncols, pp[0], H.plan[2]);
         if (err.empty()) err = build_plan(H, ir[3], H.ncols, H.nrows, pp[1], H.plan[3]);
     }
+    // colour-ordered comparison variant: same contributions as the GATHER plans, launched colour by colour
+    if (err.empty()) err = build_color_plan(H, ir[0], H.nrows, H.ncols, pp[0], H.plan[4]);
+    if (err.empty()) err = build_color_plan(H, ir[1], H.ncols, H.nrows, pp[1], H.plan[5]);
     // one-time setup of the stream-ordered pool the scratch vectors come from: keep freed memory cached
     if (A->device != BSM_DEVICE_NONE) {
         cudaMemPool_t pool;
@@ -293,6 +297,7 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
 // GATHER plans are 0/1, FUSED plans 2/3 (symmetric matrices; AUTO picks FUSED when it exists).
 int plan_index(const bsm_matrix *A, int op) {
     const int base = (op == BSM_OP_N) ? 0 : 1;
+    if (A->variant == BSM_VARIANT_COLOR && A->H.plan[4 + base].color_ok) return 4 + base;
     const bool fused = A->H.has_fused && (A->variant == BSM_VARIANT_AUTO || A->variant == BSM_VARIANT_FUSED ||
                                           A->variant == BSM_VARIANT_FUSED_TMA);
     return base + (fused ? 2 : 0);
@@ -326,6 +331,59 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
     if (HP.scratch_elems > 0)
         CUDA_TRY(cudaMallocAsync((void **)&scratch, (size_t)HP.scratch_elems * sizeof(T), st));
     constexpr int VMAX = 16 / (int)sizeof(T);
+    if (p >= 4) {
+        // colour-ordered variant: y <- beta*y, then one launch per (sweep, colour); the slices of a launch
+        // touch disjoint rows, so each accumulates straight into y (beta = 1), as the reference's tasks do
+        const int64_t nout = HP.out_dim;
+        for (int64_t j = 0; j < nrhs; ++j) {
+            MulArgs<T> a;
+            a.arena = (const T *)A->arena;
+            a.contrib = DP.contrib.p;
+            a.contrib_toff = DP.contrib_toff.p;
+            a.set_len = A->set_len.p;
+            a.set_start = A->set_start.p;
+            a.set_pool_off = A->set_pool_off.p;
+            a.pool = A->pool.p;
+            a.x = x + j * ldx;
+            a.y = y + j * ldy;
+            a.scratch = nullptr;
+            std::memcpy(&a.alpha, alpha, sizeof(T));
+            T one;
+            std::memset(&one, 0, sizeof(T));
+            if constexpr (sizeof(T) == 4) {
+                const float o = 1.f;
+                std::memcpy(&one, &o, 4);
+            } else {
+                const double o = 1.0;
+                std::memcpy(&one, &o, 8);
+            }
+            T b;
+            std::memset(&b, 0, sizeof(T));
+            if (!beta_is_false) std::memcpy(&b, beta, sizeof(T));
+            const bool prof = A->profiling && nrhs == 1;
+            if (prof) CUDA_TRY(cudaEventRecord(A->ev[0], st));
+            if (nout > 0) {
+                scale_kernel<T><<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(a.y, nout, b, beta_is_false ? 1 : 0);
+                CUDA_TRY(cudaGetLastError());
+            }
+            a.beta = one;
+            a.beta_false = 0;
+            a.conj = (op == BSM_OP_C && sizeof(T) == 16) ? 1 : 0;
+            for (size_t l = 0; l + 1 < HP.color_ptr.size(); ++l) {
+                const int32_t s0 = HP.color_ptr[l], s1 = HP.color_ptr[l + 1];
+                if (s1 == s0) continue;
+                a.slices = DP.slices.p + s0;
+                a.nslices = s1 - s0;
+                gather_gemv_kernel<T, VMAX><<<a.nslices, kThreads, 0, st>>>(a);
+                CUDA_TRY(cudaGetLastError());
+            }
+            if (prof) {
+                CUDA_TRY(cudaEventRecord(A->ev[1], st));
+                CUDA_TRY(cudaEventRecord(A->ev[2], st));
+            }
+        }
+        return 0;
+    }
     if constexpr (sizeof(T) == 8) {
         // many right-hand sides: one pass over A on the FP64 tensor cores instead of nrhs SpMV passes
         if (nrhs >= kSpmmMinRhs && HP.spmm_ok && A->variant != BSM_VARIANT_GATHER && p >= 2) {
@@ -584,6 +642,7 @@ int bsm_create_symmetric(int dtype, int64_t nrows, int64_t ncols, int64_t ndiag,
         H.nnz += dsize[d] * dsize[d];
         ir[0].push_back(ContribIR{(int32_t)d, 0, ds, ds, (int32_t)dsize[d]});
         ir[1].push_back(ContribIR{(int32_t)d, 1, ds, ds, (int32_t)dsize[d]});  // transpose(D)/adjoint(D), :225-237
+        ir[0].back().sweep = ir[1].back().sweep = 0;
         ir[2].push_back(ir[0].back());
         ir[3].push_back(ir[1].back());
     }
@@ -609,12 +668,14 @@ int bsm_create_symmetric(int dtype, int64_t nrows, int64_t ncols, int64_t ndiag,
         const int32_t blk = (int32_t)(ndiag + b);
         ir[0].push_back(ContribIR{blk, 0, rs[b], cs[b], (int32_t)om[b]});
         ir[1].push_back(ContribIR{blk, 0, rs[b], cs[b], (int32_t)om[b]});
+        ir[0].back().sweep = ir[1].back().sweep = 1;
     }
     // y[C_b] += transpose(O_b) x[R_b]: sweep 2 of A and sweep 1 of the wrappers
     for (int64_t b = 0; b < noff; ++b) {
         const int32_t blk = (int32_t)(ndiag + b);
         ir[0].push_back(ContribIR{blk, 1, cs[b], rs[b], (int32_t)on[b]});
         ir[1].push_back(ContribIR{blk, 1, cs[b], rs[b], (int32_t)on[b]});
+        ir[0].back().sweep = ir[1].back().sweep = 2;
     }
     // FUSED plans: both sweeps of a half-stored block from ONE pass over it, whenever its row segment
     // fits the fused kernel; taller blocks keep the two separate contributions
@@ -719,7 +780,7 @@ int bsm_destroy(bsm_handle h) {
     h->set_start.release();
     h->set_pool_off.release();
     h->pool.release();
-    for (int p = 0; p < 4; ++p) h->plan[p].release();
+    for (int p = 0; p < 6; ++p) h->plan[p].release();
     if (h->hx) cudaFree(h->hx);
     if (h->hy) cudaFree(h->hy);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
@@ -732,6 +793,9 @@ int bsm_destroy(bsm_handle h) {
 int bsm_set_variant(bsm_handle h, int variant) {
     if (int rc = check_handle(h)) return rc;
     if (variant < BSM_VARIANT_AUTO || variant > BSM_VARIANT_FUSED_TMA) return fail(BSM_ERR_ARG, "bad variant");
+    if (variant == BSM_VARIANT_COLOR && !(h->H.plan[4].color_ok && h->H.plan[5].color_ok))
+        return fail(BSM_ERR_UNSUPPORTED, "the colour-ordered variant needs an unrestricted handle, no repeated "
+                                         "index inside a block's index vector and at most 64 colours per sweep");
     h->variant = variant;
     return 0;
 }
@@ -888,6 +952,7 @@ int bsm_plan_stats(bsm_handle h, int op, int64_t out[12]) {
 int bsm_launch_count(bsm_handle h, int op) {
     if (!h || op < BSM_OP_N || op > BSM_OP_C) return BSM_ERR_ARG;
     const HostPlan &P = h->H.plan[plan_index(h, op)];
+    if (P.color_ok) return (int)P.color_ptr.size();      // scale kernel + one launch per (sweep, colour)
     return (P.n_fused_slices > 0 ? 1 : 0) + (P.n_warp_slices > 0 ? 1 : 0) +
            ((int64_t)P.slices.size() > P.n_fused_slices + P.n_warp_slices ? 1 : 0) + (P.gather_rows.empty() ? 0 : 1);
 }
@@ -913,7 +978,7 @@ TabView view(const std::vector<U> &v) {
 TabView table_view(bsm_handle h, int table, int plan, std::vector<int32_t> &tmp32) {
     const HostMatrix &H = h->H;
     TabView t;
-    if (plan < 0 || plan > 3) return t;
+    if (plan < 0 || plan > 5) return t;
     const HostPlan &P = H.plan[plan];
     switch (table) {
     case BSM_TAB_ARENA:
@@ -944,6 +1009,7 @@ TabView table_view(bsm_handle h, int table, int plan, std::vector<int32_t> &tmp3
     case BSM_TAB_CONTRIB_TOFF: return view(P.contrib_toff);
     case BSM_TAB_WCHUNK: return view(P.wchunk);
     case BSM_TAB_WITEM_PTR: return view(P.witem_ptr);
+    case BSM_TAB_COLOR_PTR: return view(P.color_ptr);
     }
     return t;
 }

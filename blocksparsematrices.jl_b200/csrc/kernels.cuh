@@ -1022,6 +1022,15 @@ __global__ void __launch_bounds__(kWWarps * 32) stream_warp_kernel(const WarpArg
         stream_warp_body<T, false>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0);
 }
 
+// y <- beta*y (beta === false: exact zeros, NaN/Inf in y are not propagated) — first step of the
+// colour-ordered variant, /root/reference/src/blockmatrix.jl:231 `y .*= β`.
+template <class T>
+__global__ void __launch_bounds__(256) scale_kernel(T *y, int64_t n, T beta, int beta_false) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    y[i] = beta_false ? El<T>::zero() : El<T>::mul(beta, y[i]);
+}
+
 template <class T>
 struct FinalizeArgs {
     const int32_t *rows;

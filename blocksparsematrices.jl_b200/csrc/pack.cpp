@@ -502,4 +502,89 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
     return std::string();
 }
 
+// ---------------------------------------------------------------------------- colour-ordered plan
+std::string build_color_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, int64_t out_dim,
+                             int64_t in_dim, const PlanParams &pp, HostPlan &P) {
+    const IndexSets &S = M.sets;
+    const int V = dtype_vec(M.dtype);
+    P = HostPlan();
+    P.out_dim = out_dim;
+    P.in_dim = in_dim;
+    if (pp.own_hi >= 0) return std::string();          // slabs use the atomic-free plans
+    struct Item {
+        int32_t c, sweep, color;
+    };
+    std::vector<Item> items;
+    std::vector<uint64_t> rowmask((size_t)out_dim, 0);
+    std::vector<int32_t> stamp((size_t)out_dim, -1);
+    int32_t cur_sweep = -1;
+    for (size_t c = 0; c < ir.size(); ++c) {
+        const ContribIR &ci = ir[c];
+        if (ci.sweep != cur_sweep) {                   // a new sweep starts with a clean conflict graph
+            if (ci.sweep < cur_sweep) return std::string();   // sweeps must arrive in order
+            cur_sweep = ci.sweep;
+            std::fill(rowmask.begin(), rowmask.end(), 0);
+        }
+        uint64_t used = 0;
+        for (int64_t k = 0; k < ci.out_len; ++k) {
+            const int64_t r = S.at(ci.out_set, k);
+            if (stamp[(size_t)r] == (int32_t)c) return std::string();   // repeated index inside one block
+            stamp[(size_t)r] = (int32_t)c;
+            used |= rowmask[(size_t)r];
+        }
+        if (~used == 0) return std::string();          // more than 64 colours
+        const int32_t color = __builtin_ctzll(~used);
+        for (int64_t k = 0; k < ci.out_len; ++k) rowmask[(size_t)S.at(ci.out_set, k)] |= (1ull << color);
+        items.push_back(Item{(int32_t)c, ci.sweep, color});
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
+        return a.sweep != b.sweep ? a.sweep < b.sweep : a.color < b.color;
+    });
+    // contributions stay in IR order (one group each); slices follow the launch order
+    P.group_ptr.assign(ir.size() + 1, 0);
+    for (size_t c = 0; c < ir.size(); ++c) {
+        const ContribIR &ci = ir[c];
+        const BlockSrc &b = M.blocks[ci.block];
+        bsm_contrib d;
+        d.off = M.block_off[ci.block];
+        d.m = b.m;
+        d.n = b.n;
+        d.in_set = ci.in_set;
+        d.form = ci.form;
+        d.out_len = ci.out_len;
+        d.block = ci.block;
+        P.contrib.push_back(d);
+        P.contrib_toff.push_back(-1);
+        P.group_set.push_back(ci.out_set);
+        P.group_ptr[c + 1] = (int64_t)c + 1;
+        P.applied_entries += (int64_t)b.m * b.n;
+    }
+    P.group_direct.assign(ir.size(), 1);
+    int32_t last_sweep = -1, last_color = -1;
+    for (const Item &it : items) {
+        const ContribIR &ci = ir[it.c];
+        if (it.sweep != last_sweep || it.color != last_color) {
+            P.color_ptr.push_back((int32_t)P.slices.size());
+            last_sweep = it.sweep;
+            last_color = it.color;
+        }
+        const int64_t L = ci.out_len;
+        const bool vec_ok = (P.contrib[it.c].m % V == 0) && (L % V == 0);
+        for (int64_t r0 = 0; r0 < L; r0 += kMaxSliceHeight) {
+            bsm_slice sl;
+            sl.out_set = ci.out_set;
+            sl.r0 = (int32_t)r0;
+            sl.r1 = (int32_t)std::min<int64_t>(L, r0 + kMaxSliceHeight);
+            sl.c_begin = it.c;
+            sl.c_end = it.c + 1;
+            sl.flags = kSliceDirect | (vec_ok ? kSliceVecOk : 0);
+            sl.scratch_off = 0;
+            P.slices.push_back(sl);
+        }
+    }
+    P.color_ptr.push_back((int32_t)P.slices.size());
+    P.color_ok = true;
+    return std::string();
+}
+
 }  // namespace bsm

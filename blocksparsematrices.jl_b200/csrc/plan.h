@@ -81,6 +81,9 @@ struct ContribIR {
     int32_t out_set;   // output segment (group key)
     int32_t in_set;
     int32_t out_len;
+    int32_t sweep = 0;       // sweep the contribution belongs to, numbered in IR order (symmetric: 0 diagonals,
+                             // 1 forward off-diagonals, 2 transposed off-diagonals — the reference runs the same
+                             // three sweeps, each with its own colouring); only the colour-ordered variant uses it
     int32_t fuse_tset = -1;  // >= 0: one pass over the block also yields y[fuse_tset] += op(B)^T x[out_set]
                              // (half-stored symmetric off-diagonal block); delivered through scratch
 };
@@ -99,6 +102,10 @@ struct HostPlan {
     std::vector<int32_t> witem_ptr;     // warp work items: chunk ranges cut at segment boundaries
     // multi-RHS (SpMM) path: usable when every slice is a direct warp-class slice (short segments that
     // own their rows); CTA work items = ranges of those slices, balanced by bytes
+    // colour-ordered variant (plans 4/5): slices sorted by (sweep, colour); launch l runs slices
+    // [color_ptr[l], color_ptr[l+1]) and accumulates straight into y (no two slices of a launch share a row)
+    std::vector<int32_t> color_ptr;
+    bool color_ok = false;
     bool spmm_ok = false;
     bool spmm_small = false;            // no block has more than 32 rows or columns (4-stage ring)
     std::vector<int32_t> mitem_ptr;
@@ -120,9 +127,9 @@ struct HostMatrix {
     std::vector<int64_t> block_off;    // element offsets, 128-byte aligned
     int64_t arena_elems = 0;           // including tail slack
     IndexSets sets;
-    // plan[0], plan[1]: GATHER variant for op N, op T/C. plan[2], plan[3]: FUSED variant (symmetric
-    // matrices only; empty otherwise).
-    HostPlan plan[4];
+    // plan[0], plan[1]: GATHER variant for op N, op T/C. plan[2], plan[3]: stream (TMA-staged) variant.
+    // plan[4], plan[5]: colour-ordered variant (the reference's schedule, for comparison).
+    HostPlan plan[6];
     bool has_fused = false;
 };
 
@@ -142,5 +149,13 @@ void layout_arena(HostMatrix &M);
 // Returns an empty string on success, else an error message.
 std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, int64_t out_dim,
                        int64_t in_dim, const PlanParams &pp, HostPlan &P);
+
+// Colour-ordered plan: the reference's schedule (/root/reference/src/coloring.jl:20-61 builds the conflict
+// graph "two blocks share an output row" and colours it; src/blockmatrix.jl:231-244 runs colour by
+// colour). Greedy first-fit colouring per sweep stands in for GraphsColoring (it only changes the grouping,
+// never the result). Leaves P.color_ok = false when the plan cannot be built (slab-restricted handle,
+// repeated indices inside one block's output vector, more than 64 colours).
+std::string build_color_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, int64_t out_dim,
+                             int64_t in_dim, const PlanParams &pp, HostPlan &P);
 
 }  // namespace bsm

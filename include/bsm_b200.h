@@ -62,7 +62,9 @@ typedef enum {
                                 half-stored symmetric blocks) */
     BSM_VARIANT_FUSED = 2,   /* symmetric: one pass over each half-stored block, transposed partials
                                 gathered through the transposed index */
-    BSM_VARIANT_COLOR = 3,   /* colour-ordered multi-launch (the reference's schedule, for comparison) */
+    BSM_VARIANT_COLOR = 3,   /* colour-ordered multi-launch (the reference's schedule, for comparison):
+                                y <- beta*y, then per sweep one launch per colour of a greedy colouring of the
+                                "blocks share an output row" graph, each block accumulating straight into y */
     BSM_VARIANT_FUSED_TMA = 4 /* FUSED with the blocks streamed by cp.async.bulk (TMA) into an mbarrier
                                 ring of shared-memory stages; what AUTO picks for symmetric matrices */
 } bsm_variant;
@@ -178,7 +180,9 @@ typedef enum {
     BSM_TAB_GROUP_SET = 14,   /* int32: index-set id of every output segment */
     BSM_TAB_CONTRIB_TOFF = 15,/* int64: scratch offset of the fused transposed partial of a contribution, -1 if none */
     BSM_TAB_WCHUNK = 16,      /* bsm_wchunk records: the chunk stream of the warp-stream kernel (plans 2/3) */
-    BSM_TAB_WITEM_PTR = 17    /* int32: chunk range [ptr[i], ptr[i+1]) of warp work item i */
+    BSM_TAB_WITEM_PTR = 17,   /* int32: chunk range [ptr[i], ptr[i+1]) of warp work item i */
+    BSM_TAB_COLOR_PTR = 18    /* int32: colour-ordered plans (4 = op N, 5 = op T/C): launch l runs slices
+                                 [ptr[l], ptr[l+1]) */
 } bsm_table;
 
 /* 32-byte device records (exported verbatim). */

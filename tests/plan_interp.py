@@ -42,6 +42,8 @@ class Sets:
 
 def run_plan(A, D, op, x, alpha=1.0, beta=0.0, beta_false=True, y=None, own=None, variant="auto"):
     plan = 0 if op == "N" else 1
+    if variant == "color":
+        return run_color_plan(A, D, op, x, alpha, beta, beta_false, y, plan + 4)
     fused_exists = D.table(L.TAB_SLICE, 2).size > 0
     if variant == "fused" or (variant == "auto" and fused_exists):
         assert fused_exists
@@ -218,3 +220,40 @@ def check_ring_schedule(ch, isz):
             ii += 1
         assert done == n or (live and live[0] == done), "the chunk to consume was never issued"
     assert ii == n
+
+
+def run_color_plan(A, D, op, x, alpha, beta, beta_false, y, plan):
+    """Colour-ordered variant: y <- beta*y, then launch by launch; inside a launch no row may be touched
+    twice (that is what the colouring guarantees), every slice accumulates straight into y."""
+    arena = build_arena(A, D)
+    S = Sets(D)
+    contrib = D.table(L.TAB_CONTRIB, plan)
+    slices = D.table(L.TAB_SLICE, plan)
+    cptr = D.table(L.TAB_COLOR_PTR, plan)
+    assert cptr.size >= 2 and cptr[0] == 0 and cptr[-1] == len(slices)
+    nout = A.size[0] if op == "N" else A.size[1]
+    dt = np.result_type(D.dtype, x.dtype)
+    y = np.zeros(nout, dt) if (y is None or beta_false) else beta * y
+    conj = op == "C"
+    covered = np.zeros(len(contrib), np.int64)
+    for l in range(len(cptr) - 1):
+        touched = np.zeros(nout, bool)
+        for s in slices[cptr[l]:cptr[l + 1]]:
+            assert s["c_end"] - s["c_begin"] == 1 and (s["flags"] & 1)
+            c = contrib[s["c_begin"]]
+            r0, r1 = int(s["r0"]), int(s["r1"])
+            assert 0 < r1 - r0 <= 128 and r1 <= c["out_len"]
+            covered[s["c_begin"]] += r1 - r0
+            m, n = int(c["m"]), int(c["n"])
+            Bm = arena[c["off"]:c["off"] + m * n].reshape((m, n), order="F")
+            if conj:
+                Bm = Bm.conj()
+            rows = S.idx(s["out_set"], r0, r1)
+            assert not np.any(touched[rows]), "two slices of one colour share a row"
+            touched[rows] = True
+            if c["form"] & 1:
+                y[rows] += alpha * (Bm[:, r0:r1].T @ x[S.idx(c["in_set"], 0, m)])
+            else:
+                y[rows] += alpha * (Bm[r0:r1, :] @ x[S.idx(c["in_set"], 0, n)])
+    assert np.array_equal(covered, contrib["out_len"]), "every block must be applied exactly once"
+    return y

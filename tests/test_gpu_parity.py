@@ -28,6 +28,8 @@ def battery(A, seed=0, ops=OPS, reps=2, variants=None):
     (AUTO: TMA-staged kernels) and the GATHER (direct loads) plans."""
     if variants is None and not isinstance(A, B.SymmetricBlockMatrix):
         variants = (L.VARIANT_AUTO, L.VARIANT_GATHER)
+        if A.device().table(L.TAB_COLOR_PTR, 4).size > 0:        # colour-ordered plan exists (no repeated indices)
+            variants += (L.VARIANT_COLOR,)
     if variants:
         for v in variants:
             A.device().set_variant(v)
@@ -60,9 +62,10 @@ def golden(request):
 def test_symmetric_fixture(golden):
     A = B.SymmetricBlockMatrix(golden.diagonals, golden.diagonalindices, golden.offdiagonals,
                                golden.rowindices, golden.colindices, golden.size)
-    for variant in (L.VARIANT_FUSED_TMA, L.VARIANT_FUSED, L.VARIANT_GATHER):
+    for variant in (L.VARIANT_FUSED_TMA, L.VARIANT_FUSED, L.VARIANT_GATHER, L.VARIANT_COLOR):
         A.device().set_variant(variant)
         battery(A)
+    assert A.device().launch_count("N") > 4                      # colour-ordered: scale + one launch per colour
     A.device().set_variant(L.VARIANT_AUTO)
     assert A.device().launch_count("N") == 2                     # fused kernel + finalize
     assert A.device().nnz() == B.nnz(A) == B.sparse(A).nnz      # test_symmetricblockmatrix.jl:99-107

@@ -253,6 +253,35 @@ def test_long_tform_segments_are_cut_into_column_ranges():
     assert rel(run_plan(A, D, "N", x), O.mul_bsm(OA, x.astype(np.float64), "N")) < 1e-5
 
 
+@pytest.mark.parametrize("op", OPS)
+def test_color_ordered_plans(fixture, op):
+    """Colour-ordered comparison variant: greedy colouring per sweep, launches touch disjoint rows."""
+    A = fixture
+    P = B.SymmetricBlockMatrix(A.diagonals, A.diagonalindices, A.offdiagonals, A.rowindices, A.colindices, A.size)
+    D = host_only(P)
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(A.size[1]) + 1j * rng.standard_normal(A.size[1])
+    y0 = rng.standard_normal(A.size[0]) + 1j * rng.standard_normal(A.size[0])
+    assert rel(run_plan(P, D, op, x, variant="color"), O.mul_sbm(A, x, op)) < 1e-13
+    assert rel(run_plan(P, D, op, x, 1j, 2j, False, y0.copy(), variant="color"),
+               O.mul_sbm(A, x, op, 1j, 2j, False, y0.copy())) < 1e-13
+    nl = len(D.table(L.TAB_COLOR_PTR, 4)) - 1
+    assert 3 <= nl <= 64           # three sweeps; the transposed one needs many colours (column sets overlap)
+    D.set_variant(L.VARIANT_COLOR)
+    assert D.launch_count(op) == nl + 1
+    E = O.sbm_to_bsm(A)
+    Pb = B.BlockSparseMatrix(E.blocks, E.rowindices, E.colindices, E.size)
+    assert rel(run_plan(Pb, host_only(Pb), op, x, variant="color"), O.mul_bsm(E, x, op)) < 1e-13
+
+
+def test_color_variant_refuses_repeated_indices():
+    rng = np.random.default_rng(12)
+    blocks, rows, cols = random_bsm(rng, 40, 33, 25, np.float64, contiguous=False)
+    D = host_only(B.BlockSparseMatrix(blocks, rows, cols, (40, 33)))
+    with pytest.raises(L.BsmError):
+        D.set_variant(L.VARIANT_COLOR)
+
+
 def test_errors():
     b = [np.ones((2, 2))]
     with pytest.raises(L.BsmError):      # index out of range
