@@ -92,8 +92,35 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []
+
+    def _poll(self):
+        import pynvml as N
+        h = N.nvmlDeviceGetHandleByIndex(self.index)
+        while not self._stop:
+            try:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+                rs = N.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(N, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((sm, mx, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        # NVML polled in-process every ~2 ms (the timed region lasts tens of ms); nvidia-smi -lms as fallback
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            self.nvml = N
+            self._stop = False
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
@@ -107,6 +134,19 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            N = self.nvml
+            self._stop = True
+            self.thread.join(timeout=1.0)
+            names = {"hw_slowdown": getattr(N, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(N, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            reasons = sorted(k for k, bit in names.items() if any(r & bit for _, _, r in self.samples))
+            sm = [a for a, _, _ in self.samples]
+            mx = [b for _, b, _ in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                    "reasons": reasons, "samples": len(sm), "source": "nvml polled during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -218,6 +258,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--op", default=None, choices=["N", "T", "C"], help="override the workload's op (development)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -243,6 +284,8 @@ def main():
     t0 = time.time()
     host_threads = max(1, (os.cpu_count() or 8) // max(world, 1))
     A, op, own, rb = build_workload(args.workload, args.scale, rank, world, threads=min(host_threads, 32))
+    if args.op:
+        op = args.op
     t_gen = time.time() - t0
     t0 = time.time()
     full_work = None
@@ -414,6 +457,12 @@ def main():
         ach_tf = local_work["flops"] / (k_ms * 1e-3) / 1e12
         tensor = {"bound": "tensor", "achieved": ach_tf, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": ach_tf / dgemm_tf,
                   "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (best of 5)"}
+    traffic = None
+    tfile = ROOT / "profiles" / "traffic.json"
+    if tfile.exists() and args.scale == 1.0 and world == 1 and args.variant == 0 and not args.op:
+        ent = json.loads(tfile.read_text()).get(args.workload)
+        if ent and ent["kernel"] == kernel_name:
+            traffic = ent["dram_bytes_per_launch"]     # dram__bytes_read.sum + write.sum, ncu --set full (profiles/)
     line = {
         "metric": METRIC, "value": work["bytes"] / (ms_step * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -426,7 +475,7 @@ def main():
                    "algorithmic_bytes": work["bytes"], "flops": work["flops"],
                    "gen_s": round(t_gen, 1), "pack_s": round(t_pack, 1), "plan": stats},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": kernel_name, "kernel_ms": k_ms,
+                     "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms,
                      "finalize_ms": float(np.mean(fin_ms)), "peak_source": peak_src,
                      "bytes_per_launch": local_work["bytes"]},
         "e2e": e2e,
