@@ -258,6 +258,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-gather, then multiply, on one stream")
     ap.add_argument("--op", default=None, choices=["N", "T", "C"], help="override the workload's op (development)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -293,6 +294,7 @@ def main():
         # one process per GPU: nnz-balanced block-row slabs, libbsm_b200's own NCCL communicator
         from bsm_b200.dist import Comm, SlabMatrix
         comm = Comm.from_torch(local)
+        comm.set_overlap(not args.no_overlap)
         if rb is None:        # generic partition of the full host matrix (every rank generated it)
             full_work = A.device(device=L.DEVICE_NONE).work(op, nrhs=spec.get("nrhs", 1))
             SM = SlabMatrix(A, comm, ops=(op,), variant=args.variant)
@@ -471,7 +473,9 @@ def main():
         "config": {"workload": spec["desc"], "op": op, "l2": "working set larger than L2 (no flush needed)"
                    if work["bytes"] > 4 * 126e6 else "L2 flushed? no — working set fits L2, launch-bound case",
                    "variant": {0: "auto", 1: "gather", 2: "fused", 3: "color", 4: "fused_tma"}[args.variant],
-                   "parallelism": f"block-row slabs x{world}, NCCL all-gather of x" if world > 1 else "single GPU",
+                   "parallelism": (f"block-row slabs x{world}, NCCL all-gather of x "
+                                   f"({'sequential' if args.no_overlap else 'overlapped with the rank-local slices'})")
+                   if world > 1 else "single GPU",
                    "algorithmic_bytes": work["bytes"], "flops": work["flops"],
                    "gen_s": round(t_gen, 1), "pack_s": round(t_pack, 1), "plan": stats},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

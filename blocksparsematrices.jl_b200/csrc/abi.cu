@@ -246,6 +246,11 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
         pp[0].own_hi = opt->own_row_hi;
         pp[1].own_lo = opt->own_col_lo;
         pp[1].own_hi = opt->own_col_hi;
+        // op N reads x along the columns, op T/C along the rows: the x slab a rank owns before the all-gather
+        pp[0].in_lo = opt->own_col_lo;
+        pp[0].in_hi = opt->own_col_hi;
+        pp[1].in_lo = opt->own_row_lo;
+        pp[1].in_hi = opt->own_row_hi;
         A->variant = opt->variant;
     }
     std::string err = build_plan(H, ir[0], H.nrows, H.ncols, pp[0], H.plan[0]);
@@ -303,20 +308,26 @@ int plan_index(const bsm_matrix *A, int op) {
     return base + (fused ? 2 : 0);
 }
 
+// phase 0: the whole multiply. Slab handles under bsm_mul_dist (nrhs = 1): phase 1 = the slices whose inputs
+// are rank-local (runs while x is being all-gathered), phase 2 = the remote slices + the gather pass; the
+// scratch vector allocated in phase 1 travels through *scratch_io.
 template <class T>
 int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int beta_is_false,
-               const T *x, int64_t ldx, T *y, int64_t ldy, int64_t nrhs, cudaStream_t st) {
+               const T *x, int64_t ldx, T *y, int64_t ldy, int64_t nrhs, cudaStream_t st, int phase = 0,
+               void **scratch_io = nullptr) {
     const int p = plan_index(A, op);
     const HostPlan &HP = A->H.plan[p];
     const DevPlan &DP = A->plan[p];
     T *scratch = nullptr;
+    if (phase != 0 && (nrhs != 1 || p >= 4 || !scratch_io)) return fail(BSM_ERR_ARG, "phased multiply needs nrhs = 1");
     const int32_t nfused = (int32_t)HP.n_fused_slices;
     const int32_t nwarp = (int32_t)HP.n_warp_slices;
     const bool use_tma = A->variant != BSM_VARIANT_FUSED;
     if (nfused > 0 || nwarp > 0) {
-        static bool attr_done[3] = {false, false, false};
+        static bool attr_done_dev[64][3] = {};
         const int di = sizeof(T) == 4 ? 0 : sizeof(T) == 8 ? 1 : 2;
-        if (!attr_done[di]) {
+        bool &attr_done_ref = attr_done_dev[A->device & 63][di];
+        if (!attr_done_ref) {
             CUDA_TRY(cudaFuncSetAttribute(sym_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)fused_smem_bytes<T>()));
             CUDA_TRY(cudaFuncSetAttribute(sym_fused_tma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -325,11 +336,23 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
                                           (int)fused_tma_smem_bytes<T>()));
             CUDA_TRY(cudaFuncSetAttribute(stream_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)stream_warp_smem_bytes<T>()));
-            attr_done[di] = true;
+            attr_done_ref = true;
         }
     }
-    if (HP.scratch_elems > 0)
+    if (phase == 2)
+        scratch = (T *)*scratch_io;
+    else if (HP.scratch_elems > 0)
         CUDA_TRY(cudaMallocAsync((void **)&scratch, (size_t)HP.scratch_elems * sizeof(T), st));
+    if (phase == 1) *scratch_io = scratch;
+    // slice / item ranges of this phase
+    const int32_t nitems_all = HP.witem_ptr.empty() ? 0 : (int32_t)HP.witem_ptr.size() - 1;
+    const int32_t ngather_all = (int32_t)HP.slices.size() - nfused - nwarp;
+    const int32_t f0 = phase == 2 ? (int32_t)HP.n_fused_local : 0;
+    const int32_t f1 = phase == 1 ? (int32_t)HP.n_fused_local : nfused;
+    const int32_t w0 = phase == 2 ? (int32_t)HP.n_warp_items_local : 0;
+    const int32_t w1 = phase == 1 ? (int32_t)HP.n_warp_items_local : nitems_all;
+    const int32_t g0 = phase == 2 ? (int32_t)HP.n_gather_local : 0;
+    const int32_t g1 = phase == 1 ? (int32_t)HP.n_gather_local : ngather_all;
     constexpr int VMAX = 16 / (int)sizeof(T);
     if (p >= 4) {
         // colour-ordered variant: y <- beta*y, then one launch per (sweep, colour); the slices of a launch
@@ -467,43 +490,45 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
         const bool prof = A->profiling && nrhs == 1;
         if (A->profiling && nrhs > 1 && j == 0) CUDA_TRY(cudaEventRecord(A->ev[0], st));
         if (prof) CUDA_TRY(cudaEventRecord(A->ev[0], st));
-        if (nfused > 0) {
+        if (f1 > f0) {
+            MulArgs<T> b = a;
+            b.slices = a.slices + f0;
             if (use_tma)
                 if (HP.fused_general)
-                    sym_fused_tma_kernel<T, true><<<nfused, kPThreads, fused_tma_smem_bytes<T>(), st>>>(a);
+                    sym_fused_tma_kernel<T, true><<<f1 - f0, kPThreads, fused_tma_smem_bytes<T>(), st>>>(b);
                 else
-                    sym_fused_tma_kernel<T, false><<<nfused, kPThreads, fused_tma_smem_bytes<T>(), st>>>(a);
+                    sym_fused_tma_kernel<T, false><<<f1 - f0, kPThreads, fused_tma_smem_bytes<T>(), st>>>(b);
             else
-                sym_fused_kernel<T><<<nfused, kFThreads, fused_smem_bytes<T>(), st>>>(a);
+                sym_fused_kernel<T><<<f1 - f0, kFThreads, fused_smem_bytes<T>(), st>>>(b);
             CUDA_TRY(cudaGetLastError());
         }
-        if (nwarp > 0) {
+        if (w1 > w0) {
             WarpArgs<T> w;
             w.arena = (const unsigned char *)A->arena;
             w.chunks = DP.wchunk.p;
-            w.item_ptr = DP.witem_ptr.p;
+            w.item_ptr = DP.witem_ptr.p + w0;
             w.pool = A->pool.p;
             w.x = a.x;
             w.y = a.y;
             w.scratch = scratch;
             w.alpha = a.alpha;
             w.beta = a.beta;
-            w.nitems = (int32_t)HP.witem_ptr.size() - 1;
+            w.nitems = w1 - w0;
             w.beta_false = a.beta_false;
             w.conj = a.conj;
             stream_warp_kernel<T><<<(unsigned)((w.nitems + kWWarps - 1) / kWWarps), kWWarps * 32,
                                     stream_warp_smem_bytes<T>(), st>>>(w);
             CUDA_TRY(cudaGetLastError());
         }
-        if (a.nslices > nfused + nwarp) {
+        if (g1 > g0) {
             MulArgs<T> b = a;
-            b.slices = a.slices + nfused + nwarp;
-            b.nslices = a.nslices - nfused - nwarp;
+            b.slices = a.slices + nfused + nwarp + g0;
+            b.nslices = g1 - g0;
             gather_gemv_kernel<T, VMAX><<<b.nslices, kThreads, 0, st>>>(b);
             CUDA_TRY(cudaGetLastError());
         }
         if (prof) CUDA_TRY(cudaEventRecord(A->ev[1], st));
-        const int64_t ng = (int64_t)HP.gather_rows.size();
+        const int64_t ng = phase == 1 ? 0 : (int64_t)HP.gather_rows.size();
         if (ng > 0) {
             FinalizeArgs<T> f;
             f.rows = DP.gather_rows.p;
@@ -525,7 +550,7 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             CUDA_TRY(cudaEventRecord(A->ev[2], st));
         }
     }
-    if (scratch) CUDA_TRY(cudaFreeAsync(scratch, st));
+    if (scratch && phase != 1) CUDA_TRY(cudaFreeAsync(scratch, st));
     return 0;
 }
 
@@ -850,6 +875,36 @@ int bsm_mul(bsm_handle h, int op, const void *alpha, const void *beta, int beta_
                                 (cplx *)y_dev, ldy, nrhs, st);
     }
 }
+
+}  // extern "C"
+
+// internal (dist.cu): one phase of a slab multiply, see launch_mul. Returns 1 through *has_remote when the plan
+// of `op` holds remote slices at all (otherwise a plain bsm_mul after the gather is just as good).
+int bsm_plan_has_remote(bsm_handle h, int op) {
+    if (!h || op < BSM_OP_N || op > BSM_OP_C) return 0;
+    const int p = plan_index(h, op);
+    return (p < 4 && h->H.plan[p].has_remote) ? 1 : 0;
+}
+int bsm_mul_phase(bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false, const void *x_dev,
+                  void *y_dev, void *stream, int phase, void **scratch_io) {
+    if (int rc = check_handle(h)) return rc;
+    if (h->device == BSM_DEVICE_NONE) return fail(BSM_ERR_CUDA, "host-only handle");
+    DeviceGuard g(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (h->H.dtype) {
+    case BSM_F32:
+        return launch_mul<float>(h, op, alpha, beta, beta_is_false, (const float *)x_dev, 0, (float *)y_dev, 0, 1, st,
+                                 phase, scratch_io);
+    case BSM_F64:
+        return launch_mul<double>(h, op, alpha, beta, beta_is_false, (const double *)x_dev, 0, (double *)y_dev, 0, 1,
+                                  st, phase, scratch_io);
+    default:
+        return launch_mul<cplx>(h, op, alpha, beta, beta_is_false, (const cplx *)x_dev, 0, (cplx *)y_dev, 0, 1, st,
+                                phase, scratch_io);
+    }
+}
+
+extern "C" {
 
 int bsm_mul_host(bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
                  const void *x_host, int64_t ldx, void *y_host, int64_t ldy, int64_t nrhs) {

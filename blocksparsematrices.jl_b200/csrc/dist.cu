@@ -74,9 +74,16 @@ thread_local std::string g_dist_err;
 // abi.cu owns the thread-local error string of bsm_last_error(); this hook lets dist.cu set it.
 void bsm_set_error(const std::string &msg);
 
+int bsm_plan_has_remote(bsm_handle h, int op);
+int bsm_mul_phase(bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false, const void *x_dev,
+                  void *y_dev, void *stream, int phase, void **scratch_io);
+
 struct bsm_comm_s {
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0, device = 0;
+    cudaStream_t comm_stream = nullptr;     // the all-gather runs here, beside the rank-local slices
+    cudaEvent_t ev_ready = nullptr, ev_gathered = nullptr;
+    int overlap = 1;
 };
 
 namespace {
@@ -127,12 +134,31 @@ int bsm_dist_init(const void *id128, int nranks, int rank, int device, bsm_comm 
         delete c;
         return dfail(BSM_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl().GetErrorString(r));
     }
+    // highest priority: the NCCL blocks must get SM slots as soon as compute blocks retire, not after the
+    // whole compute grid has drained
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_gathered, cudaEventDisableTiming) != cudaSuccess) {
+        bsm_dist_destroy(c);
+        return dfail(BSM_ERR_CUDA, "could not create the communication stream");
+    }
     *out = c;
+    return 0;
+}
+
+int bsm_dist_set_overlap(bsm_comm c, int on) {
+    if (!c) return dfail(BSM_ERR_ARG, "null communicator");
+    c->overlap = on ? 1 : 0;
     return 0;
 }
 
 int bsm_dist_destroy(bsm_comm c) {
     if (!c) return 0;
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    if (c->ev_ready) cudaEventDestroy(c->ev_ready);
+    if (c->ev_gathered) cudaEventDestroy(c->ev_gathered);
     if (c->comm && nccl().CommDestroy) nccl().CommDestroy(c->comm);
     delete c;
     return 0;
@@ -190,6 +216,19 @@ int bsm_mul_dist(bsm_comm c, bsm_handle h, int op, const void *alpha, const void
                  void *x_dev, int64_t ldx, void *y_dev, int64_t ldy, int64_t nrhs, const int64_t *in_cuts,
                  void *stream) {
     if (!c || !h) return dfail(BSM_ERR_ARG, "null communicator or handle");
+    if (c->nranks > 1 && c->overlap && nrhs == 1 && bsm_plan_has_remote(h, op)) {
+        // overlap: the all-gather runs on the communicator's stream while the slices fed by this rank's own
+        // x slab run on the caller's stream; the remote slices and the gather pass follow the all-gather
+        cudaStream_t st = (cudaStream_t)stream;
+        if (cudaEventRecord(c->ev_ready, st) != cudaSuccess || cudaStreamWaitEvent(c->comm_stream, c->ev_ready, 0) != cudaSuccess)
+            return dfail(BSM_ERR_CUDA, "event record/wait failed");
+        if (int rc = bsm_dist_allgather_rows(c, bsm_dtype_of(h), x_dev, ldx, 1, in_cuts, (void *)c->comm_stream)) return rc;
+        if (cudaEventRecord(c->ev_gathered, c->comm_stream) != cudaSuccess) return dfail(BSM_ERR_CUDA, "event record failed");
+        void *scratch = nullptr;
+        if (int rc = bsm_mul_phase(h, op, alpha, beta, beta_is_false, x_dev, y_dev, stream, 1, &scratch)) return rc;
+        if (cudaStreamWaitEvent(st, c->ev_gathered, 0) != cudaSuccess) return dfail(BSM_ERR_CUDA, "event wait failed");
+        return bsm_mul_phase(h, op, alpha, beta, beta_is_false, x_dev, y_dev, stream, 2, &scratch);
+    }
     if (c->nranks > 1) {
         if (int rc = bsm_dist_allgather_rows(c, bsm_dtype_of(h), x_dev, ldx, nrhs, in_cuts, stream)) return rc;
     }

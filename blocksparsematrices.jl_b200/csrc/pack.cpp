@@ -178,6 +178,7 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
         bsm_slice s;
         int64_t work;
         int64_t order;
+        bool remote = false;
     };
     std::vector<Tmp> tmp;
     const int64_t hmin = std::max<int64_t>(1, 128 / s);
@@ -344,13 +345,45 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
         }
     }
 
+    // 5b. slab handles: a slice is remote when one of its inputs is outside the x range this rank owns
+    //     before the all-gather (the fused transposed partial also reads x at the segment's own rows)
+    if (pp.in_hi >= 0) {
+        std::vector<int8_t> set_local(S.len.size(), -1);
+        auto is_local = [&](int32_t set) -> bool {
+            if (set_local[set] < 0) {
+                bool ok = true;
+                if (S.start[set] >= 0) {
+                    ok = S.start[set] >= pp.in_lo && (int64_t)S.start[set] + S.len[set] <= pp.in_hi;
+                } else {
+                    for (int64_t k = 0; k < S.len[set] && ok; ++k) {
+                        const int64_t r = S.at(set, k);
+                        ok = r >= pp.in_lo && r < pp.in_hi;
+                    }
+                }
+                set_local[set] = ok ? 1 : 0;
+            }
+            return set_local[set] == 1;
+        };
+        for (auto &t : tmp) {
+            for (int32_t c = t.s.c_begin; c < t.s.c_end && !t.remote; ++c) {
+                if (!is_local(P.contrib[c].in_set)) t.remote = true;
+                if (contrib_tset[(size_t)c] >= 0 && !is_local(t.s.out_set)) t.remote = true;
+            }
+            if (t.remote) {
+                t.s.flags |= kSliceRemote;
+                P.has_remote = true;
+            }
+        }
+    }
+
     // 6. schedule: CTA-kernel slices first (heaviest first), then the warp-stream slices in creation
     //    order (= arena order, so every warp streams a contiguous run of HBM), then the gather slices
-    //    (heaviest first); stable
+    //    (heaviest first); inside every class the rank-local slices come before the remote ones; stable
     auto cls = [](const Tmp &t) { return (t.s.flags & kSliceFused) ? 0 : (t.s.flags & kSliceWarp) ? 1 : 2; };
     std::stable_sort(tmp.begin(), tmp.end(), [&](const Tmp &a, const Tmp &b) {
         const int ca = cls(a), cb = cls(b);
         if (ca != cb) return ca < cb;
+        if (a.remote != b.remote) return !a.remote;
         if (ca == 1) return false;
         return a.work > b.work;
     });
@@ -366,6 +399,12 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
         }
         if (t.s.flags & kSliceFused) P.n_fused_slices++;
         if (t.s.flags & kSliceWarp) P.n_warp_slices++;
+        if (!t.remote) {
+            if (t.s.flags & kSliceFused)
+                P.n_fused_local++;
+            else if (!(t.s.flags & kSliceWarp))
+                P.n_gather_local++;
+        }
     }
 
     // 7. chunk stream of the warp slices: every chunk is one bulk copy of whole block columns and
@@ -434,12 +473,18 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
             } else {
                 we.out = sl.scratch_off;
             }
-            if (item_bytes >= target) {
+            // work items never mix local and remote segments: the local items run while x is gathered
+            const bool last_local = !(sl.flags & kSliceRemote) && i + 1 < P.n_fused_slices + P.n_warp_slices &&
+                                    (P.slices[i + 1].flags & kSliceRemote);
+            if (item_bytes >= target || last_local) {
                 P.witem_ptr.push_back((int32_t)P.wchunk.size());
                 item_bytes = 0;
             }
+            if (!(sl.flags & kSliceRemote)) P.n_warp_items_local = (int64_t)P.witem_ptr.size() - 1;
         }
         if (P.witem_ptr.back() != (int32_t)P.wchunk.size()) P.witem_ptr.push_back((int32_t)P.wchunk.size());
+        if (!(P.slices[P.n_fused_slices + P.n_warp_slices - 1].flags & kSliceRemote))
+            P.n_warp_items_local = (int64_t)P.witem_ptr.size() - 1;   // no remote warp segment at all
         // static shared-memory schedule of every work item: chunks are placed in a circular byte
         // buffer in issue order; a chunk that does not fit waits for the oldest live chunks
         for (size_t it = 0; it + 1 < P.witem_ptr.size(); ++it) {

@@ -31,6 +31,8 @@ static_assert(sizeof(bsm_wchunk) == 32, "bsm_wchunk must be 32 bytes");
 constexpr int kSliceDirect = 1;
 constexpr int kSliceVecOk = 2;
 constexpr int kSliceFused = 4;          // handled by sym_fused_kernel (whole segment, <= kFusedMaxRows rows)
+constexpr int kSliceRemote = 16;        // some input of the slice lies outside the rank's own x range (slab handles):
+                                        // it must wait for the all-gather, the other slices overlap with it
 constexpr int kSliceWarp = 8;           // handled by stream_warp_kernel (whole segment, <= kWarpMaxRows rows)
 constexpr int kFusedMaxRows = 256;
 constexpr int kFusedMaxTRows = 1024;    // tallest T-form block the CTA kernel stages (x window in shared memory)
@@ -96,6 +98,9 @@ struct HostPlan {
     std::vector<int64_t> contrib_toff;  // scratch offset of the fused transposed partial, -1 if none
     std::vector<bsm_slice> slices;      // fused slices first, each class sorted by decreasing work
     int64_t n_fused_slices = 0;
+    // slab handles: within every kernel class the slices whose inputs are all rank-local come first
+    int64_t n_fused_local = 0, n_warp_items_local = 0, n_gather_local = 0;
+    bool has_remote = false;
     bool fused_general = false;         // some CTA-kernel slice is a column sub-range or holds a tall T-form block
     int64_t n_warp_slices = 0;          // follow the fused slices; the rest go to gather_gemv_kernel
     std::vector<bsm_wchunk> wchunk;     // chunk stream of the warp slices, in slice order
@@ -135,6 +140,7 @@ struct HostMatrix {
 
 struct PlanParams {
     int64_t own_lo = 0, own_hi = -1;   // owned output range, hi < 0: everything
+    int64_t in_lo = 0, in_hi = -1;     // range of x this rank owns before the all-gather, hi < 0: everything
     int64_t work_target_bytes = 512 << 10;
     bool fused = false;                // stream plan: segments of <= kFusedMaxRows rows go to the TMA-staged
                                        // kernels (CTA kernel, or warp-stream kernel when <= kWarpMaxRows), unsplit

@@ -39,6 +39,9 @@ class Comm:
         dist.broadcast_object_list(box, src=0)
         return cls(box[0], world, rank, device)
 
+    def set_overlap(self, on: bool):
+        L.check(L.lib().bsm_dist_set_overlap(self._h, int(on)))
+
     def nccl_version(self) -> int:
         v = c_int(0)
         L.check(L.lib().bsm_dist_info(self._h, None, None, byref(v)))

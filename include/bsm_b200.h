@@ -202,7 +202,9 @@ typedef struct {
     int32_t out_set;     /* index set of the output segment */
     int32_t r0, r1;      /* output sub-range [r0, r1) of the segment handled by this work item */
     int32_t c_begin, c_end; /* contributions [c_begin, c_end) */
-    int32_t flags;       /* bit0: direct (writes y), else partial sums to scratch; bit1: vector loads ok;
+    int32_t flags;       /* bit4: slab handle only — some input lies outside the rank's own x range (runs after the
+                            all-gather; the other slices overlap with it);
+                            bit0: direct (writes y), else partial sums to scratch; bit1: vector loads ok;
                             bit2: handled by the TMA-staged CTA kernel (whole segment of <= 256 rows, or a
                             column sub-range of an all-T-form segment); bit3: whole segment of <= 64 rows,
                             handled by the warp-stream kernel through the bsm_wchunk stream */
@@ -249,6 +251,10 @@ typedef struct bsm_comm_s *bsm_comm;
 int bsm_dist_unique_id(void *id128);       /* rank 0: ncclGetUniqueId; ship the 128 bytes to every rank */
 int bsm_dist_init(const void *id128, int nranks, int rank, int device, bsm_comm *out);
 int bsm_dist_destroy(bsm_comm c);
+/* on (default): bsm_mul_dist runs the all-gather on the communicator's own stream while the slices whose
+ * inputs lie in this rank's x slab run on the caller's stream; the remote slices follow. off: gather, then
+ * multiply, on one stream (comparison). */
+int bsm_dist_set_overlap(bsm_comm c, int on);
 int bsm_dist_info(bsm_comm c, int *nranks, int *rank, int *nccl_version);
 /* In-place all-gather of the row slabs of a column-major (rows x nrhs, leading dimension ldx) DEVICE
  * array: on return every rank holds all rows. cuts has nranks+1 entries (0-based, non-decreasing). */

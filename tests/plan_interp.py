@@ -40,7 +40,9 @@ class Sets:
         return self.pool[self.poff[s] + lo:self.poff[s] + hi].astype(np.int64)
 
 
-def run_plan(A, D, op, x, alpha=1.0, beta=0.0, beta_false=True, y=None, own=None, variant="auto"):
+def run_plan(A, D, op, x, alpha=1.0, beta=0.0, beta_false=True, y=None, own=None, variant="auto", in_own=None):
+    """in_own = (lo, hi): slab handle under bsm_mul_dist — the slices NOT flagged remote (bit 4) run before the
+    all-gather has delivered anything, so they are executed here with x poisoned (NaN) outside [lo, hi)."""
     plan = 0 if op == "N" else 1
     if variant == "color":
         return run_color_plan(A, D, op, x, alpha, beta, beta_false, y, plan + 4)
@@ -67,10 +69,19 @@ def run_plan(A, D, op, x, alpha=1.0, beta=0.0, beta_false=True, y=None, own=None
     for k in range(1, len(slices)):      # fused slices come first
         assert not ((slices[k]["flags"] & 4) and not (slices[k - 1]["flags"] & 4))
     written = np.zeros(nout, np.int32)
-    cls = [0 if (s["flags"] & 4) else 1 if (s["flags"] & 8) else 2 for s in slices]
-    assert cls == sorted(cls), "slice classes must be ordered: CTA-stream, warp-stream, gather"
-    run_warp_stream(D, plan, arena, S, slices, x, y, scratch, written, conj, alpha, beta, beta_false, dt)
+    cls = [(0 if (s["flags"] & 4) else 1 if (s["flags"] & 8) else 2, 1 if (s["flags"] & 16) else 0) for s in slices]
+    assert cls == sorted(cls), "slices must be ordered by class (CTA-stream, warp-stream, gather), local before remote"
+    x_full = x
+    if in_own is not None:
+        x_local = x.astype(np.result_type(x.dtype, np.float32), copy=True)
+        x_local[:in_own[0]] = np.nan
+        x_local[in_own[1]:] = np.nan
+    else:
+        assert own is not None or not any(s["flags"] & 16 for s in slices), "remote slices only exist in slab handles"
+        x_local = x
+    run_warp_stream(D, plan, arena, S, slices, x_full, x_local, y, scratch, written, conj, alpha, beta, beta_false, dt)
     for s in slices:
+        x = x_full if (s["flags"] & 16) else x_local
         if s["flags"] & 8:
             continue            # executed from the chunk stream above
         r0, r1 = int(s["r0"]), int(s["r1"])
@@ -137,7 +148,7 @@ def run_plan(A, D, op, x, alpha=1.0, beta=0.0, beta_false=True, y=None, own=None
     return y
 
 
-def run_warp_stream(D, plan, arena, S, slices, x, y, scratch, written, conj, alpha, beta, beta_false, dt):
+def run_warp_stream(D, plan, arena, S, slices, x_full, x_local, y, scratch, written, conj, alpha, beta, beta_false, dt):
     """Executes the bsm_wchunk stream exactly as stream_warp_kernel does: per work item, chunk by chunk,
     reading the arena BYTES the bulk copy would fetch."""
     chunks = D.table(L.TAB_WCHUNK, plan)
@@ -150,9 +161,16 @@ def run_warp_stream(D, plan, arena, S, slices, x, y, scratch, written, conj, alp
     raw = arena.view(np.uint8)
     isz = arena.dtype.itemsize
     nseg = 0
+    seg = 0
     for it in range(len(iptr) - 1):
         acc = None
         check_ring_schedule(chunks[iptr[it]:iptr[it + 1]], isz)
+        # a work item is all-local or all-remote (local items run while x is being gathered)
+        nseg_item = int(np.sum((chunks[iptr[it]:iptr[it + 1]]["flags"] & 16) != 0))
+        kinds = {bool(wsl[seg + k]["flags"] & 16) for k in range(nseg_item)}
+        assert len(kinds) == 1, "a warp work item mixes local and remote segments"
+        x = x_full if kinds.pop() else x_local
+        seg += nseg_item
         for q in range(iptr[it], iptr[it + 1]):
             c = chunks[q]
             fl, m, nc, Lseg = int(c["flags"]), int(c["m"]), int(c["ncols"]), int(c["seg_len"])

@@ -57,7 +57,10 @@ def _worker(rank, world, port, kind, q):
         xg = xr.numpy()
         xg = xg.view(np.complex128) if x.dtype.kind == "c" else xg
         y = np.zeros(n, xg.dtype)
-        run_plan(S, D, op, xg, y=y, own=(lo, hi))
+        run_plan(S, D, op, xg, y=y, own=(lo, hi), in_own=(lo, hi))   # local slices must not need gathered x
+        sl = D.table(L.TAB_SLICE, (0 if op == "N" else 1) + 2)
+        nloc = int(np.sum((sl["flags"] & 16) == 0))
+        assert 0 < nloc < len(sl), "a slab should have both rank-local and remote slices"
         ys = [None] * world
         dist.all_gather_object(ys, (lo, hi, y[lo:hi]))
         full = np.zeros(n, y.dtype)

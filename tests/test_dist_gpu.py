@@ -56,6 +56,14 @@ def _worker(rank, world, port, q):
             y = torch.zeros_like(x)
             SM.mul(op, x, y)
             torch.cuda.synchronize()
+            # gather-then-multiply on one stream gives bitwise the same slab as the overlapped schedule
+            comm.set_overlap(False)
+            x2 = torch.from_numpy(xh.T.copy()).cuda().T if nrhs > 1 else torch.from_numpy(xh).cuda()
+            y2 = torch.zeros_like(x2)
+            SM.mul(op, x2, y2)
+            torch.cuda.synchronize()
+            comm.set_overlap(True)
+            assert torch.equal(y, y2), "overlapped and sequential schedules differ"
             assert np.array_equal(x.cpu().numpy(), xt), "all-gather did not replicate x"
             got = y.cpu().numpy()[lo:hi]
             if nrhs == 1:
