@@ -258,6 +258,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--broadcasts", action="store_true", help="N > 1: grouped in-place broadcasts instead of the all-gather")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-gather, then multiply, on one stream")
     ap.add_argument("--op", default=None, choices=["N", "T", "C"], help="override the workload's op (development)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -295,6 +296,7 @@ def main():
         from bsm_b200.dist import Comm, SlabMatrix
         comm = Comm.from_torch(local)
         comm.set_overlap(not args.no_overlap)
+        comm.set_collective(args.broadcasts)
         if rb is None:        # generic partition of the full host matrix (every rank generated it)
             full_work = A.device(device=L.DEVICE_NONE).work(op, nrhs=spec.get("nrhs", 1))
             SM = SlabMatrix(A, comm, ops=(op,), variant=args.variant)

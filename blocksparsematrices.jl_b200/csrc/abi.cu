@@ -253,10 +253,18 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
         pp[1].in_hi = opt->own_row_hi;
         A->variant = opt->variant;
     }
+    // work-item budget of the stream plans: no CTA should hold more than ~1/8 of a resident slot's fair share (LPT tail <= ~6 %)
+    const int64_t total_bytes = [&] {
+        int64_t t = 0;
+        for (const auto &b : H.blocks) t += (int64_t)b.m * b.n * dtype_size(H.dtype);
+        return t;
+    }();
+    const int64_t split = std::max<int64_t>(256 << 10, total_bytes / (148 * 2 * 8));
     std::string err = build_plan(H, ir[0], H.nrows, H.ncols, pp[0], H.plan[0]);
     if (err.empty()) err = build_plan(H, ir[1], H.ncols, H.nrows, pp[1], H.plan[1]);
     if (H.has_fused) {
         pp[0].fused = pp[1].fused = true;
+        pp[0].split_bytes = pp[1].split_bytes = split;
         pp[0].warp_stream = pp[1].warp_stream = H.kind != BSM_KIND_SYMMETRIC;
         if (err.empty()) err = build_plan(H, ir[2], H.nrows, H.ncols, pp[0], H.plan[2]);
         if (err.empty()) err = build_plan(H, ir[3], H.ncols, H.nrows, pp[1], H.plan[3]);
@@ -308,9 +316,10 @@ int plan_index(const bsm_matrix *A, int op) {
     return base + (fused ? 2 : 0);
 }
 
-// phase 0: the whole multiply. Slab handles under bsm_mul_dist (nrhs = 1): phase 1 = the slices whose inputs
-// are rank-local (runs while x is being all-gathered), phase 2 = the remote slices + the gather pass; the
-// scratch vector allocated in phase 1 travels through *scratch_io.
+// phase 0: the whole multiply. Slab handles under bsm_mul_dist (nrhs = 1, scratch owned by the caller and passed
+// through *scratch_io): phase 1 = the slices whose inputs are rank-local (run while x is being all-gathered),
+// phase 2 = the remote slices (on a second stream, so the two grids fill each other's tails), phase 3 = the
+// gather pass.
 template <class T>
 int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int beta_is_false,
                const T *x, int64_t ldx, T *y, int64_t ldy, int64_t nrhs, cudaStream_t st, int phase = 0,
@@ -339,20 +348,19 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             attr_done_ref = true;
         }
     }
-    if (phase == 2)
+    if (phase != 0)
         scratch = (T *)*scratch_io;
     else if (HP.scratch_elems > 0)
         CUDA_TRY(cudaMallocAsync((void **)&scratch, (size_t)HP.scratch_elems * sizeof(T), st));
-    if (phase == 1) *scratch_io = scratch;
     // slice / item ranges of this phase
     const int32_t nitems_all = HP.witem_ptr.empty() ? 0 : (int32_t)HP.witem_ptr.size() - 1;
     const int32_t ngather_all = (int32_t)HP.slices.size() - nfused - nwarp;
     const int32_t f0 = phase == 2 ? (int32_t)HP.n_fused_local : 0;
-    const int32_t f1 = phase == 1 ? (int32_t)HP.n_fused_local : nfused;
+    const int32_t f1 = phase == 3 ? 0 : phase == 1 ? (int32_t)HP.n_fused_local : nfused;
     const int32_t w0 = phase == 2 ? (int32_t)HP.n_warp_items_local : 0;
-    const int32_t w1 = phase == 1 ? (int32_t)HP.n_warp_items_local : nitems_all;
+    const int32_t w1 = phase == 3 ? 0 : phase == 1 ? (int32_t)HP.n_warp_items_local : nitems_all;
     const int32_t g0 = phase == 2 ? (int32_t)HP.n_gather_local : 0;
-    const int32_t g1 = phase == 1 ? (int32_t)HP.n_gather_local : ngather_all;
+    const int32_t g1 = phase == 3 ? 0 : phase == 1 ? (int32_t)HP.n_gather_local : ngather_all;
     constexpr int VMAX = 16 / (int)sizeof(T);
     if (p >= 4) {
         // colour-ordered variant: y <- beta*y, then one launch per (sweep, colour); the slices of a launch
@@ -528,7 +536,7 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             CUDA_TRY(cudaGetLastError());
         }
         if (prof) CUDA_TRY(cudaEventRecord(A->ev[1], st));
-        const int64_t ng = phase == 1 ? 0 : (int64_t)HP.gather_rows.size();
+        const int64_t ng = (phase == 1 || phase == 2) ? 0 : (int64_t)HP.gather_rows.size();
         if (ng > 0) {
             FinalizeArgs<T> f;
             f.rows = DP.gather_rows.p;
@@ -550,7 +558,7 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             CUDA_TRY(cudaEventRecord(A->ev[2], st));
         }
     }
-    if (scratch && phase != 1) CUDA_TRY(cudaFreeAsync(scratch, st));
+    if (scratch && phase == 0) CUDA_TRY(cudaFreeAsync(scratch, st));
     return 0;
 }
 
@@ -884,6 +892,10 @@ int bsm_plan_has_remote(bsm_handle h, int op) {
     if (!h || op < BSM_OP_N || op > BSM_OP_C) return 0;
     const int p = plan_index(h, op);
     return (p < 4 && h->H.plan[p].has_remote) ? 1 : 0;
+}
+int64_t bsm_plan_scratch_bytes(bsm_handle h, int op) {
+    if (!h || op < BSM_OP_N || op > BSM_OP_C) return 0;
+    return h->H.plan[plan_index(h, op)].scratch_elems * (int64_t)dtype_size(h->H.dtype);
 }
 int bsm_mul_phase(bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false, const void *x_dev,
                   void *y_dev, void *stream, int phase, void **scratch_io) {

@@ -59,6 +59,16 @@ int32_t IndexSets::add_vector(const int64_t *idx1, int64_t n, int64_t limit) {
     return id;
 }
 
+int32_t IndexSets::add_subset(int32_t set, int64_t k0, int64_t n) {
+    if (k0 == 0 && n == len[set]) return set;
+    if (start[set] >= 0) return add_range((int64_t)start[set] + k0, n);
+    const int32_t id = (int32_t)len.size();
+    len.push_back((int32_t)n);
+    start.push_back(-1);
+    pool_off.push_back(pool_off[set] + k0);
+    return id;
+}
+
 // ---------------------------------------------------------------------------- arena
 void layout_arena(HostMatrix &M) {
     const int64_t s = dtype_size(M.dtype);
@@ -76,9 +86,9 @@ void layout_arena(HostMatrix &M) {
 }
 
 // ---------------------------------------------------------------------------- plan
-std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, int64_t out_dim,
+std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t out_dim,
                        int64_t in_dim, const PlanParams &pp, HostPlan &P) {
-    const IndexSets &S = M.sets;
+    IndexSets &S = M.sets;
     const int64_t s = dtype_size(M.dtype);
     const int V = dtype_vec(M.dtype);
     const int64_t own_lo = pp.own_hi < 0 ? 0 : pp.own_lo;
@@ -127,7 +137,6 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
     P.group_ptr.assign(G + 1, 0);
     P.group_set.assign(gset.begin(), gset.end());
     for (size_t g = 0; g < G; ++g) {
-        P.group_ptr[g + 1] = P.group_ptr[g] + (int64_t)members[g].size();
         for (int32_t c : members[g]) {
             const ContribIR &ci = ir[c];
             const BlockSrc &b = M.blocks[ci.block];
@@ -143,12 +152,32 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
                 if (ci.form != 0 || !pp.fused || S.len[gset[g]] > kFusedMaxRows || S.len[ci.fuse_tset] < b.n)
                     return "bad fused contribution";
             }
-            contrib_tset.push_back(ci.fuse_tset);
             if (ci.out_len > S.len[gset[g]]) return "contribution longer than its output segment";
             if (S.len[ci.in_set] < (ci.form == 0 ? b.n : b.m)) return "input set shorter than block";
-            P.contrib.push_back(d);
             P.applied_entries += (int64_t)b.m * b.n * (ci.fuse_tset >= 0 ? 2 : 1);
+            // a wide N-form block of a CTA-kernel segment that alone exceeds the work-item budget is entered as
+            // several column ranges (own input sub-set, own transposed partial): the slicer below can then
+            // hand them to different CTAs
+            const int64_t bytes = (int64_t)b.m * b.n * s;
+            if (pp.fused && pp.split_bytes > 0 && ci.form == 0 && S.len[gset[g]] <= kFusedMaxRows &&
+                S.len[gset[g]] > kWarpMaxRows && bytes > pp.split_bytes + pp.split_bytes / 2 && b.n >= 8) {
+                const int64_t k = (bytes + pp.split_bytes - 1) / pp.split_bytes;
+                const int64_t cn = std::max<int64_t>(4, ((b.n + k - 1) / k + 3) / 4 * 4);
+                for (int64_t c0 = 0; c0 < b.n; c0 += cn) {
+                    const int64_t w = std::min<int64_t>(cn, b.n - c0);
+                    bsm_contrib e = d;
+                    e.off = d.off + c0 * b.m;
+                    e.n = (int32_t)w;
+                    e.in_set = S.add_subset(ci.in_set, c0, w);
+                    P.contrib.push_back(e);
+                    contrib_tset.push_back(ci.fuse_tset >= 0 ? S.add_subset(ci.fuse_tset, c0, w) : -1);
+                }
+                continue;
+            }
+            contrib_tset.push_back(ci.fuse_tset);
+            P.contrib.push_back(d);
         }
+        P.group_ptr[g + 1] = (int64_t)P.contrib.size();
     }
 
     // 3. ownership: first come claims; a group is direct iff none of its rows is claimed, it has no
@@ -223,18 +252,35 @@ std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, in
             continue;
         }
         if (pp.fused && L <= kFusedMaxRows && t_ok) {
-            // one work item for the whole segment: the CTA kernel keeps all its rows in registers
-            Tmp t;
-            t.s.out_set = gset[g];
-            t.s.r0 = 0;
-            t.s.r1 = (int32_t)L;
-            t.s.c_begin = (int32_t)P.group_ptr[g];
-            t.s.c_end = (int32_t)P.group_ptr[g + 1];
-            t.s.flags = (P.group_direct[g] ? kSliceDirect : 0) | kSliceFused;
-            t.s.scratch_off = 0;
-            t.work = W;
-            t.order = (int64_t)tmp.size();
-            tmp.push_back(t);
+            // whole segment in one CTA (all its rows in registers). A segment far heavier than the work-item
+            // budget is cut along its contribution list: the first item stays direct, the others deliver
+            // partial vectors through the gather lists (deterministic, fixed order)
+            const int64_t budget = pp.split_bytes > 0 ? pp.split_bytes : (int64_t)1 << 62;
+            int32_t cb0 = (int32_t)P.group_ptr[g];
+            const int32_t cend = (int32_t)P.group_ptr[g + 1];
+            bool first_item = true;
+            while (cb0 < cend || first_item) {
+                int32_t ce = cb0;
+                int64_t wk = 0;
+                while (ce < cend && (ce == cb0 || wk + (int64_t)P.contrib[ce].m * P.contrib[ce].n * s <= budget + budget / 2 ||
+                                     W <= budget + budget / 2)) {
+                    wk += (int64_t)P.contrib[ce].m * P.contrib[ce].n * s;
+                    ++ce;
+                }
+                Tmp t;
+                t.s.out_set = gset[g];
+                t.s.r0 = 0;
+                t.s.r1 = (int32_t)L;
+                t.s.c_begin = cb0;
+                t.s.c_end = ce;
+                t.s.flags = ((P.group_direct[g] && first_item) ? kSliceDirect : 0) | kSliceFused;
+                t.s.scratch_off = 0;
+                t.work = wk;
+                t.order = (int64_t)tmp.size();
+                tmp.push_back(t);
+                first_item = false;
+                cb0 = ce;
+            }
             continue;
         }
         if (pp.fused && all_t && t_ok && !any_fuse) {

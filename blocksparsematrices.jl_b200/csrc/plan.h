@@ -64,6 +64,8 @@ struct IndexSets {
     int32_t add_vector(const int64_t *idx1, int64_t n, int64_t limit);
     // 0-based contiguous range
     int32_t add_range(int64_t start0, int64_t n);
+    // positions [k0, k0+n) of an existing set as a set of its own (shares the pool entries)
+    int32_t add_subset(int32_t set, int64_t k0, int64_t n);
     inline int64_t at(int32_t s, int64_t k) const {
         return start[s] >= 0 ? (int64_t)start[s] + k : (int64_t)pool[pool_off[s] + k];
     }
@@ -146,6 +148,9 @@ struct PlanParams {
                                        // kernels (CTA kernel, or warp-stream kernel when <= kWarpMaxRows), unsplit
     bool warp_stream = true;           // short segments may go to the warp-stream kernel (off for symmetric
                                        // matrices: their leaf segments stay with the CTA kernel, one launch)
+    int64_t split_bytes = 0;           // stream plans: a segment of the CTA kernel streaming more than ~1.5x this is
+                                       // cut into several work items (wide blocks by column ranges, partial sums
+                                       // through the gather lists) so that no single CTA sets the makespan; 0: off
     int64_t witem_bytes = 0;           // target bytes per warp work item (0: derived from the total)
 };
 
@@ -153,7 +158,8 @@ struct PlanParams {
 void layout_arena(HostMatrix &M);
 // Groups contributions, decides direct vs scratch ownership, cuts slices, builds the gather lists.
 // Returns an empty string on success, else an error message.
-std::string build_plan(const HostMatrix &M, const std::vector<ContribIR> &ir, int64_t out_dim,
+// (adds index sets for column sub-ranges of split blocks: call before the tables are uploaded)
+std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t out_dim,
                        int64_t in_dim, const PlanParams &pp, HostPlan &P);
 
 // Colour-ordered plan: the reference's schedule (/root/reference/src/coloring.jl:20-61 builds the conflict

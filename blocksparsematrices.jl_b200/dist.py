@@ -42,6 +42,9 @@ class Comm:
     def set_overlap(self, on: bool):
         L.check(L.lib().bsm_dist_set_overlap(self._h, int(on)))
 
+    def set_collective(self, use_broadcasts: bool):
+        L.check(L.lib().bsm_dist_set_collective(self._h, int(use_broadcasts)))
+
     def nccl_version(self) -> int:
         v = c_int(0)
         L.check(L.lib().bsm_dist_info(self._h, None, None, byref(v)))

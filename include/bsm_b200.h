@@ -242,8 +242,9 @@ int bsm_table_copy(bsm_handle h, int table, int plan, void *dst, int64_t dst_byt
 /* ---- single-box multi-GPU: block-row slabs + NCCL all-gather of x ------------------
  * One process per GPU. Rank r builds its handle from the blocks of its slab with
  * bsm_options.own_row_* / own_col_* = its output range, keeps a FULL-length x on its device and owns
- * rows [cuts[r], cuts[r+1]) of it. bsm_mul_dist first replicates x (one NCCL group of in-place broadcasts
- * per rank and right-hand side, directly on the column-major array — slabs are uneven), then multiplies;
+ * rows [cuts[r], cuts[r+1]) of it. bsm_mul_dist replicates x (slabs are uneven: equal-chunk staging buffer, one
+ * ncclAllGather, strided copies back) while the slices fed by the rank's own x slab already run, then
+ * multiplies the rest;
  * each rank writes only its own slice of y. NCCL is bound at run time (dlopen "libnccl.so.2"). The
  * reference has no counterpart (single process). */
 typedef struct bsm_comm_s *bsm_comm;
@@ -255,6 +256,9 @@ int bsm_dist_destroy(bsm_comm c);
  * inputs lie in this rank's x slab run on the caller's stream; the remote slices follow. off: gather, then
  * multiply, on one stream (comparison). */
 int bsm_dist_set_overlap(bsm_comm c, int on);
+/* 0 (default): equal-chunk staging + one ncclAllGather; 1: one NCCL group of in-place broadcasts per rank and
+ * right-hand side (no staging; 10x slower on 8 GPUs, kept for comparison). */
+int bsm_dist_set_collective(bsm_comm c, int use_broadcasts);
 int bsm_dist_info(bsm_comm c, int *nranks, int *rank, int *nccl_version);
 /* In-place all-gather of the row slabs of a column-major (rows x nrhs, leading dimension ldx) DEVICE
  * array: on return every rank holds all rows. cuts has nranks+1 entries (0-based, non-decreasing). */

@@ -58,11 +58,14 @@ def _worker(rank, world, port, q):
             torch.cuda.synchronize()
             # gather-then-multiply on one stream gives bitwise the same slab as the overlapped schedule
             comm.set_overlap(False)
+            comm.set_collective(True)          # and the grouped-broadcast collective replicates x identically
             x2 = torch.from_numpy(xh.T.copy()).cuda().T if nrhs > 1 else torch.from_numpy(xh).cuda()
             y2 = torch.zeros_like(x2)
             SM.mul(op, x2, y2)
             torch.cuda.synchronize()
             comm.set_overlap(True)
+            comm.set_collective(False)
+            assert torch.equal(x, x2)
             assert torch.equal(y, y2), "overlapped and sequential schedules differ"
             assert np.array_equal(x.cpu().numpy(), xt), "all-gather did not replicate x"
             got = y.cpu().numpy()[lo:hi]

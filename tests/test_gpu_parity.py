@@ -127,6 +127,13 @@ def test_c2_shape(permuted, dtype):
         battery(A, reps=1)
 
 
+def test_c2_heavy_segments_split():
+    A = G.symmetric_nearfield(seed=20, n=6000, leaf_min=150, leaf_max=250, k_near=4)
+    sl = A.device().table(L.TAB_SLICE, 2)
+    assert np.unique(sl["out_set"], return_counts=True)[1].max() > 1
+    battery(A, reps=1)
+
+
 def test_c2_tall_leaves_mix_fused_and_gather_kernels():
     A = G.symmetric_nearfield(seed=19, n=20000, leaf_min=150, leaf_max=400, k_near=3)
     sl = A.device().table(L.TAB_SLICE, 2)

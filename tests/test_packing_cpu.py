@@ -282,6 +282,30 @@ def test_color_variant_refuses_repeated_indices():
         D.set_variant(L.VARIANT_COLOR)
 
 
+@pytest.mark.parametrize("op", OPS)
+def test_heavy_segments_are_split_across_work_items(op):
+    """A leaf segment streaming far more than the work-item budget is cut: wide off-diagonal blocks enter the
+    plan as column ranges (own input sub-set, own transposed partial), the first item stays direct, the
+    others deliver partial vectors through the gather lists."""
+    from bsm_b200 import generators as G
+    A = G.symmetric_nearfield(seed=23, n=2400, leaf_min=150, leaf_max=250, k_near=4)
+    D = host_only(A)
+    OA = O.OSBM(A.diagonals, A.diagonalindices, A.offdiagonals, A.rowindices, A.colindices, A.size)
+    plan = 2 if op == "N" else 3
+    sl = D.table(L.TAB_SLICE, plan)
+    cf = D.table(L.TAB_CONTRIB, plan)
+    assert len(cf) > len(A.diagonals) + len(A.offdiagonals)          # some blocks were split by columns
+    segs, counts = np.unique(sl["out_set"], return_counts=True)
+    assert counts.max() > 1                                           # several work items for one segment
+    for sset in segs[counts > 1]:
+        assert ((sl["flags"][sl["out_set"] == sset] & 1) != 0).sum() <= 1   # at most one of them writes y directly
+    rng = np.random.default_rng(13)
+    x = rng.standard_normal(2400) + 1j * rng.standard_normal(2400)
+    y0 = rng.standard_normal(2400) + 1j * rng.standard_normal(2400)
+    assert rel(run_plan(A, D, op, x), O.mul_sbm(OA, x, op)) < 1e-13
+    assert rel(run_plan(A, D, op, x, 1j, 2j, False, y0.copy()), O.mul_sbm(OA, x, op, 1j, 2j, False, y0.copy())) < 1e-13
+
+
 def test_errors():
     b = [np.ones((2, 2))]
     with pytest.raises(L.BsmError):      # index out of range
