@@ -270,3 +270,50 @@ def test_spmm_deterministic():
     A = G.blocksparse_uniform(seed=35, n=6400, nblocks=1500, bs=32)
     X = np.asfortranarray(np.random.default_rng(0).standard_normal((6400, 64)))
     assert np.array_equal(A * X, A * X)
+
+
+# ---- edge cases: empty and ragged inputs, rectangular operators, degenerate blocks ---------------------------
+def test_empty_and_degenerate_inputs():
+    rng = np.random.default_rng(21)
+    # no blocks at all: y = beta*y (strong zero for beta === false)
+    E = B.BlockSparseMatrix([], [], [], (7, 5))
+    assert np.array_equal(E * np.ones(5), np.zeros(7))
+    y0 = rng.standard_normal(7)
+    assert np.allclose(B.mul_(y0.copy(), E, np.ones(5), 2.0, 3.0), 3.0 * y0)
+    assert np.array_equal(B.transpose(E) * np.ones(7), np.zeros(5))
+    # zero-row / zero-column blocks next to real ones, 1x1 blocks, a single wide and a single tall block
+    blocks = [np.zeros((0, 3)), rng.standard_normal((1, 1)), np.zeros((2, 0)), rng.standard_normal((1, 9)),
+              rng.standard_normal((6, 1)), rng.standard_normal((3, 4))]
+    rows = [np.zeros(0, np.int64), [4], [1, 2], [5], [1, 2, 3, 4, 5, 6], [2, 3, 4]]
+    cols = [[1, 2, 3], [9], np.zeros(0, np.int64), np.arange(1, 10), [3], [5, 6, 7, 8]]
+    battery(B.BlockSparseMatrix(blocks, rows, cols, (6, 9)), reps=1)
+    # rectangular operators, more rows than columns and the reverse, F32 / F64 / CF64
+    for dt in (np.float32, np.float64, np.complex128):
+        for shape in ((50, 13), (13, 50)):
+            bl, r, c = [], [], []
+            for _ in range(12):
+                m, n = rng.integers(1, 8, 2)
+                r0, c0 = rng.integers(1, shape[0] - m + 2), rng.integers(1, shape[1] - n + 2)
+                b = rng.standard_normal((m, n)) + (1j * rng.standard_normal((m, n)) if np.dtype(dt).kind == "c" else 0)
+                bl.append(np.asfortranarray(b.astype(dt)))
+                r.append(np.arange(r0, r0 + m))
+                c.append(np.arange(c0, c0 + n))
+            battery(B.BlockSparseMatrix(bl, r, c, shape), reps=1)
+    # symmetric matrix without off-diagonal blocks, and one with a single leaf
+    d = [np.asfortranarray(rng.standard_normal((4, 4)) + 1j * rng.standard_normal((4, 4))) for _ in range(3)]
+    d = [x + x.T for x in d]
+    idx = [np.arange(1, 5), np.arange(5, 9), np.arange(9, 13)]
+    battery(B.SymmetricBlockMatrix(d, idx, [], [], [], (12, 12)), reps=1)
+    battery(B.SymmetricBlockMatrix(d[:1], idx[:1], [], [], [], (4, 4)), reps=1)
+    # VBCRS with a single 1x1 block in a larger matrix
+    battery(B.VariableBlockCompressedRowStorage([np.array([[2.5]])], [3], [2], (5, 4)), reps=1)
+
+
+def test_dimension_mismatch_and_dtype_errors():
+    A = G.blocksparse_uniform(seed=36, n=640, nblocks=20, bs=32)
+    with pytest.raises(ValueError):
+        A * np.ones(641)
+    with pytest.raises(ValueError):
+        B.mul_(np.zeros(639), A, np.ones(640))
+    with pytest.raises(TypeError):
+        B.BlockSparseMatrix([np.ones((2, 2), np.int32)], [[1, 2]], [[1, 2]], (2, 2)).device()
