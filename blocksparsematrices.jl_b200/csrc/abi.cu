@@ -68,11 +68,14 @@ struct DevPlan {
     DevBuf<int32_t> gather_rows;
     DevBuf<int64_t> gather_ptr, gather_pos;
     DevBuf<bsm_wchunk> wchunk;
-    DevBuf<int32_t> witem_ptr, mitem_ptr;
+    DevBuf<int32_t> witem_ptr, mitem_ptr, muncovered;
+    DevBuf<bsm_slice> mslices;
     void release() {
         wchunk.release();
         witem_ptr.release();
         mitem_ptr.release();
+        muncovered.release();
+        mslices.release();
         contrib.release();
         contrib_toff.release();
         slices.release();
@@ -226,6 +229,8 @@ int upload_tables(bsm_matrix *A) {
         if (int rc = A->plan[p].wchunk.upload(H.plan[p].wchunk)) return rc;
         if (int rc = A->plan[p].witem_ptr.upload(H.plan[p].witem_ptr)) return rc;
         if (int rc = A->plan[p].mitem_ptr.upload(H.plan[p].mitem_ptr)) return rc;
+        if (int rc = A->plan[p].muncovered.upload(H.plan[p].muncovered)) return rc;
+        if (int rc = A->plan[p].mslices.upload(H.plan[p].mslices)) return rc;
     }
     return 0;
 }
@@ -265,6 +270,10 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
     if (H.has_fused) {
         pp[0].fused = pp[1].fused = true;
         pp[0].split_bytes = pp[1].split_bytes = split;
+        // small (L2-resident, latency-bound) problems: one warp work item per ~1/2368 of the matrix, down to
+        // single blocks, so that all 148 x 16 warps have something to stream
+        if (total_bytes < (int64_t)148 * 16 * (32 << 10))
+            pp[0].wsplit_bytes = pp[1].wsplit_bytes = std::max<int64_t>(4 << 10, total_bytes / (148 * 16));
         pp[0].warp_stream = pp[1].warp_stream = H.kind != BSM_KIND_SYMMETRIC;
         if (err.empty()) err = build_plan(H, ir[2], H.nrows, H.ncols, pp[0], H.plan[2]);
         if (err.empty()) err = build_plan(H, ir[3], H.ncols, H.nrows, pp[1], H.plan[3]);
@@ -427,7 +436,7 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             SpmmArgs m;
             m.arena = (const double *)A->arena;
             m.contrib = DP.contrib.p;
-            m.slices = DP.slices.p;
+            m.slices = DP.mslices.p;
             m.item_ptr = DP.mitem_ptr.p;
             m.set_start = A->set_start.p;
             m.set_pool_off = A->set_pool_off.p;
@@ -449,24 +458,12 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             spmm_dmma_kernel<<<grid, kMThreads, spmm_smem_bytes(HP.spmm_small), st>>>(m);
             CUDA_TRY(cudaGetLastError());
             if (prof) CUDA_TRY(cudaEventRecord(A->ev[1], st));
-            const int64_t ng = (int64_t)HP.gather_rows.size();
-            if (ng > 0) {
-                // rows no block touches: y = beta*y (there are no partial sums on this path)
-                FinalizeArgs<T> f;
-                f.rows = DP.gather_rows.p;
-                f.ptr = DP.gather_ptr.p;
-                f.pos = DP.gather_pos.p;
-                f.scratch = nullptr;
-                std::memcpy(&f.alpha, alpha, sizeof(T));
-                std::memcpy(&f.beta, &m.beta, sizeof(T));
-                f.n = ng;
-                f.ldy = ldy;
-                f.beta_false = m.beta_false;
-                f.y = y;
+            const int64_t nu = (int64_t)HP.muncovered.size();
+            if (nu > 0) {   // rows no block touches: y = beta*y
                 for (int64_t jb = 0; jb < nrhs; jb += 65535) {   // grid.y limit
-                    f.y = y + jb * ldy;
-                    dim3 fg((unsigned)((ng + 255) / 256), (unsigned)std::min<int64_t>(65535, nrhs - jb));
-                    gather_finalize_kernel<T><<<fg, 256, 0, st>>>(f);
+                    dim3 fg((unsigned)((nu + 255) / 256), (unsigned)std::min<int64_t>(65535, nrhs - jb));
+                    spmm_uncovered_kernel<<<fg, 256, 0, st>>>(DP.muncovered.p, nu, (double *)y + jb * ldy, ldy, m.beta,
+                                                              m.beta_false);
                 }
                 CUDA_TRY(cudaGetLastError());
             }

@@ -210,6 +210,7 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
         bool remote = false;
     };
     std::vector<Tmp> tmp;
+    std::vector<uint8_t> group_warp(G, 0);
     const int64_t hmin = std::max<int64_t>(1, 128 / s);
     for (size_t g = 0; g < G; ++g) {
         const int64_t L = S.len[gset[g]];
@@ -237,18 +238,41 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
         }
         if (pp.fused && pp.warp_stream && L <= kWarpMaxRows && small_ok && !any_fuse && entries > 0 &&
             S.pool.size() < (size_t)0x7fffffff) {
-            // whole segment streamed by ONE warp of stream_warp_kernel
-            Tmp t;
-            t.s.out_set = gset[g];
-            t.s.r0 = 0;
-            t.s.r1 = (int32_t)L;
-            t.s.c_begin = (int32_t)P.group_ptr[g];
-            t.s.c_end = (int32_t)P.group_ptr[g + 1];
-            t.s.flags = (P.group_direct[g] ? kSliceDirect : 0) | kSliceWarp;
-            t.s.scratch_off = 0;
-            t.work = W;
-            t.order = (int64_t)tmp.size();
-            tmp.push_back(t);
+            // whole segment streamed by ONE warp of stream_warp_kernel. Small problems (wsplit_bytes > 0) cut
+            // a segment with several blocks into several work items: the first stays direct, the others
+            // deliver partial vectors through the gather lists
+            group_warp[g] = 1;
+            const int64_t budget = pp.wsplit_bytes > 0 ? pp.wsplit_bytes : (int64_t)1 << 62;
+            int32_t cb0 = (int32_t)P.group_ptr[g];
+            const int32_t cend = (int32_t)P.group_ptr[g + 1];
+            bool first_item = true;
+            while (cb0 < cend) {
+                int32_t ce = cb0;
+                int64_t wk = 0;
+                while (ce < cend) {
+                    const int64_t add = (int64_t)P.contrib[ce].m * P.contrib[ce].n * s;
+                    if (wk > 0 && add > 0 && wk + add > budget + budget / 2 && W > budget + budget / 2) break;
+                    wk += add;
+                    ++ce;
+                }
+                // trailing empty blocks stay with the last item that carries data
+                int64_t rest = 0;
+                for (int32_t c = ce; c < cend; ++c) rest += (int64_t)P.contrib[c].m * P.contrib[c].n;
+                if (rest == 0) ce = cend;
+                Tmp t;
+                t.s.out_set = gset[g];
+                t.s.r0 = 0;
+                t.s.r1 = (int32_t)L;
+                t.s.c_begin = cb0;
+                t.s.c_end = ce;
+                t.s.flags = ((P.group_direct[g] && first_item) ? kSliceDirect : 0) | kSliceWarp;
+                t.s.scratch_off = 0;
+                t.work = wk;
+                t.order = (int64_t)tmp.size();
+                tmp.push_back(t);
+                first_item = false;
+                cb0 = ce;
+            }
             continue;
         }
         if (pp.fused && L <= kFusedMaxRows && t_ok) {
@@ -461,7 +485,7 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
             for (int32_t c = P.slices[i].c_begin; c < P.slices[i].c_end; ++c)
                 total += (int64_t)P.contrib[c].m * P.contrib[c].n * s;
         int64_t target = pp.witem_bytes;
-        if (target <= 0) target = std::min<int64_t>(1 << 20, std::max<int64_t>(16 << 10, total / (148 * 8 * 6)));
+        if (target <= 0) target = std::min<int64_t>(1 << 20, std::max<int64_t>(4 << 10, total / (148 * 8 * 6)));
         P.witem_ptr.push_back(0);
         int64_t item_bytes = 0;
         for (int64_t i = P.n_fused_slices; i < P.n_fused_slices + P.n_warp_slices; ++i) {
@@ -567,9 +591,9 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
     }
     // 8. multi-RHS work items: the SpMM kernel walks slices/contributions itself (its producer warp runs
     //    ahead of the tensor-core consumers), so an item is just a range of slices
-    P.spmm_ok = P.n_warp_slices > 0 && P.n_warp_slices == (int64_t)P.slices.size() && P.gather_pos.empty();
-    for (const auto &sl : P.slices)
-        if (!(sl.flags & kSliceDirect)) P.spmm_ok = false;
+    P.spmm_ok = G > 0;
+    for (size_t g = 0; g < G; ++g)
+        if (S.len[gset[g]] > 0 && !(group_warp[g] && P.group_direct[g])) P.spmm_ok = false;
     if (P.spmm_ok) {
         int64_t total = 0;
         P.spmm_small = true;
@@ -577,18 +601,32 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
             total += (int64_t)c.m * c.n * s;
             if (c.m > 32 || ((c.form & kFormT) && c.n > 32)) P.spmm_small = false;
         }
+        for (size_t g = 0; g < G; ++g) {
+            if (S.len[gset[g]] == 0) continue;
+            bsm_slice sl;
+            sl.out_set = gset[g];
+            sl.r0 = 0;
+            sl.r1 = S.len[gset[g]];
+            sl.c_begin = (int32_t)P.group_ptr[g];
+            sl.c_end = (int32_t)P.group_ptr[g + 1];
+            sl.flags = kSliceDirect | kSliceWarp;
+            sl.scratch_off = 0;
+            P.mslices.push_back(sl);
+        }
+        for (int64_t r = own_lo; r < own_hi; ++r)
+            if (!claimed[(size_t)r]) P.muncovered.push_back((int32_t)r);
         const int64_t target = std::max<int64_t>(128 << 10, total / (148 * 2 * 8));
         P.mitem_ptr.push_back(0);
         int64_t acc = 0;
-        for (size_t i = 0; i < P.slices.size(); ++i) {
-            for (int32_t c = P.slices[i].c_begin; c < P.slices[i].c_end; ++c)
+        for (size_t i = 0; i < P.mslices.size(); ++i) {
+            for (int32_t c = P.mslices[i].c_begin; c < P.mslices[i].c_end; ++c)
                 acc += (int64_t)P.contrib[c].m * P.contrib[c].n * s;
             if (acc >= target) {
                 P.mitem_ptr.push_back((int32_t)(i + 1));
                 acc = 0;
             }
         }
-        if (P.mitem_ptr.back() != (int32_t)P.slices.size()) P.mitem_ptr.push_back((int32_t)P.slices.size());
+        if (P.mitem_ptr.back() != (int32_t)P.mslices.size()) P.mitem_ptr.push_back((int32_t)P.mslices.size());
     }
     return std::string();
 }

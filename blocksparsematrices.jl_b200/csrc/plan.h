@@ -114,6 +114,8 @@ struct HostPlan {
     std::vector<int32_t> color_ptr;
     bool color_ok = false;
     bool spmm_ok = false;
+    std::vector<bsm_slice> mslices;     // SpMM: one (direct, whole-segment) slice per block row, never split
+    std::vector<int32_t> muncovered;    // SpMM: owned rows no block touches (y <- beta*y there)
     bool spmm_small = false;            // no block has more than 32 rows or columns (4-stage ring)
     std::vector<int32_t> mitem_ptr;
     std::vector<int32_t> gather_rows;
@@ -151,6 +153,9 @@ struct PlanParams {
     int64_t split_bytes = 0;           // stream plans: a segment of the CTA kernel streaming more than ~1.5x this is
                                        // cut into several work items (wide blocks by column ranges, partial sums
                                        // through the gather lists) so that no single CTA sets the makespan; 0: off
+    int64_t wsplit_bytes = 0;          // small (L2-resident) problems: a warp-stream segment streaming more than ~1.5x
+                                       // this is cut along its block list into several work items (partial sums
+                                       // through the gather lists) to expose enough parallelism; 0: off
     int64_t witem_bytes = 0;           // target bytes per warp work item (0: derived from the total)
 };
 

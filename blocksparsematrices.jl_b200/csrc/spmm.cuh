@@ -330,6 +330,15 @@ __global__ void __launch_bounds__(kMThreads, 2) spmm_dmma_kernel(const SpmmArgs 
         spmm_consumer(a, msm, full, empty, j0, ncol);
 }
 
+// rows no block touches: y <- beta*y for every right-hand side (blockIdx.y)
+__global__ void __launch_bounds__(256) spmm_uncovered_kernel(const int32_t *rows, int64_t n, double *y, int64_t ldy,
+                                                             double beta, int beta_false) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double *p = y + (int64_t)blockIdx.y * ldy + rows[i];
+    *p = beta_false ? 0.0 : beta * (*p);
+}
+
 inline int spmm_stage_bytes(bool small) { return (small ? kMABytesSmall : kMABytesBig) + kMXBytes + kMHdrBytes; }
 inline int spmm_stages(bool small) {
     const int n = (kMSmemBudget - 2 * kMMaxStages * 8) / spmm_stage_bytes(small);

@@ -231,7 +231,8 @@ def test_warp_stream_schedule_c3_shape(dtype):
     for op in OPS:
         st = D.plan_stats(op)
         assert st["slices"]["stream_warp_kernel"] > 0 and st["slices"]["gather_gemv_kernel"] == 0
-        assert st["warp_items"] > 1 and D.launch_count(op) == 1
+        # small problem: multi-block segments are cut into several work items (+ the gather pass)
+        assert st["warp_items"] > 1 and D.launch_count(op) in (1, 2)
         x = rng.standard_normal(30000).astype(dtype)
         ref = O.mul_vbcrs(OV, x.astype(np.complex128 if np.dtype(dtype).kind == "c" else np.float64), op)
         assert rel(run_plan(V, D, op, x), ref) < tol
