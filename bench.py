@@ -386,6 +386,8 @@ def main():
     D.set_profiling(True)
     main_ms, fin_ms = [], []
     for _ in range(max(5, min(args.steps, 20))):
+        if l2_resident:
+            flush.zero_()
         D.mul(op, x_full, y_dev)
         a, b = D.profile()
         main_ms.append(a)

@@ -803,6 +803,74 @@ __device__ __forceinline__ void bulk_g2s_plain(void *dst_smem, const void *src, 
                  : "memory");
 }
 
+// FP64 tensor-core instruction: D(8x8) += A(8x4, row) * B(4x8, col). Fragments: a = A[lane/4][lane%4],
+// b = B[lane%4][lane/4], c0/c1 = C[lane/4][2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// T-form chunk in Float64 on the tensor cores: t[j] = sum_r B[r, j] x[r] as (B^T tile, 8 columns x 4 rows) times
+// a B-operand whose 8 columns all hold x[r] — 7/8 of the DMMA is wasted, but one DMMA replaces 32 FMAs AND the
+// whole shuffle butterfly of the scalar path (which makes T-form twice as instruction-heavy as N-form), and the
+// DMMA pipe is idle in an SpMV anyway. NJT = 8-column tiles of the chunk.
+template <int NJT>
+__device__ __forceinline__ void wchunk_tform_dmma(const double *__restrict__ sm, const double *__restrict__ xin,
+                                                  int32_t m, int32_t nc, int32_t oc, int lane, double *ts) {
+    const int g = lane >> 2, tg = lane & 3;
+    double c[NJT][2];
+    const double *ap[NJT];
+    bool jok[NJT];
+#pragma unroll
+    for (int t = 0; t < NJT; ++t) {
+        c[t][0] = c[t][1] = 0.0;
+        const int32_t j = 8 * t + g;
+        jok[t] = j < nc;
+        ap[t] = sm + (jok[t] ? j : 0) * m + tg;
+    }
+    const int32_t nfull = m >> 2;
+#pragma unroll 2
+    for (int32_t kt = 0; kt < nfull; ++kt) {
+        const double b = xin[4 * kt + tg];
+#pragma unroll
+        for (int t = 0; t < NJT; ++t) {
+            double a = 0.0;
+            if (jok[t]) a = ap[t][4 * kt];
+            dmma_m8n8k4(c[t][0], c[t][1], a, b);
+        }
+    }
+    if (m & 3) {
+        const bool rok = (4 * nfull + tg) < m;
+        const double b = rok ? xin[4 * nfull + tg] : 0.0;
+#pragma unroll
+        for (int t = 0; t < NJT; ++t) {
+            double a = 0.0;
+            if (rok && jok[t]) a = ap[t][4 * nfull];
+            dmma_m8n8k4(c[t][0], c[t][1], a, b);
+        }
+    }
+    if (tg == 0) {
+#pragma unroll
+        for (int t = 0; t < NJT; ++t)
+            if (jok[t]) ts[oc + 8 * t + g] += c[t][0];
+    }
+}
+
+__device__ __forceinline__ void wchunk_tform_dmma_dispatch(const double *sm, const double *xin, int32_t m, int32_t nc,
+                                                           int32_t oc, int lane, double *ts) {
+    switch ((nc + 7) >> 3) {
+    case 1: wchunk_tform_dmma<1>(sm, xin, m, nc, oc, lane, ts); break;
+    case 2: wchunk_tform_dmma<2>(sm, xin, m, nc, oc, lane, ts); break;
+    case 3: wchunk_tform_dmma<3>(sm, xin, m, nc, oc, lane, ts); break;
+    case 4: wchunk_tform_dmma<4>(sm, xin, m, nc, oc, lane, ts); break;
+    case 5: wchunk_tform_dmma<5>(sm, xin, m, nc, oc, lane, ts); break;
+    case 6: wchunk_tform_dmma<6>(sm, xin, m, nc, oc, lane, ts); break;
+    case 7: wchunk_tform_dmma<7>(sm, xin, m, nc, oc, lane, ts); break;
+    default: wchunk_tform_dmma<8>(sm, xin, m, nc, oc, lane, ts); break;
+    }
+}
+
 // One chunk (nc whole columns of an m-row block, column-major in shared memory) of the warp-stream
 // kernel. TWO: the block has more than 32 rows, lanes also own row lane+32.
 template <class T, bool CONJ, bool TWO>
@@ -955,7 +1023,16 @@ __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned 
         __syncwarp();
         mbar_wait(&full[ci & (kWNB - 1)], (uint32_t)((ci / kWNB) & 1));
         const T *sm = reinterpret_cast<const T *>(cbase + d0.delta());
-        if (m > 32)
+        bool done_tc = false;
+        if constexpr (sizeof(T) == 8) {
+            if (tform) {   // Float64 T-form: tensor-core path (no shuffle butterfly)
+                wchunk_tform_dmma_dispatch(reinterpret_cast<const double *>(sm), reinterpret_cast<const double *>(xin),
+                                           m, nc, d0.out_col(), lane, reinterpret_cast<double *>(ts));
+                done_tc = true;
+            }
+        }
+        if (done_tc) {
+        } else if (m > 32)
             wchunk_compute<T, CONJ, true>(sm, xin, m, nc, tform, d0.out_col(), lane, acc0, acc1, ts);
         else
             wchunk_compute<T, CONJ, false>(sm, xin, m, nc, tform, d0.out_col(), lane, acc0, acc1, ts);

@@ -65,11 +65,6 @@ struct alignas(16) SpmmHdr {
 
 __device__ __forceinline__ int spmm_ldpad(int m) { return m + ((12 - (m & 7)) & 7); }  // smallest >= m with ld % 8 == 4
 
-__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
 
 // Copies `nrun` runs of `len` consecutive doubles each, global -> shared, with the 32 lanes of the
 // producer warp: run r goes from src + r*sstride to dst + r*dstride. wide: 16-byte pieces (len even,
