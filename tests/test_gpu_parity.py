@@ -317,3 +317,44 @@ def test_dimension_mismatch_and_dtype_errors():
         B.mul_(np.zeros(639), A, np.ones(640))
     with pytest.raises(TypeError):
         B.BlockSparseMatrix([np.ones((2, 2), np.int32)], [[1, 2]], [[1, 2]], (2, 2)).device()
+
+
+# ---- seeded fuzz through the real kernels (same structures as the CPU plan-interpreter fuzz) --------------------
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_blocksparse(seed):
+    rng = np.random.default_rng(100 + seed)
+    dtype = [np.float64, np.complex128, np.float32][seed % 3]
+    contiguous = seed % 2 == 0
+    nrows, ncols = int(rng.integers(150, 400)), int(rng.integers(150, 400))
+    blocks, rows, cols = [], [], []
+    for _ in range(int(rng.integers(20, 60))):
+        m, n = min(int(rng.integers(1, 91)), nrows), min(int(rng.integers(1, 91)), ncols)
+        if contiguous:
+            r0, c0 = int(rng.integers(1, nrows - m + 2)), int(rng.integers(1, ncols - n + 2))
+            r, c = np.arange(r0, r0 + m), np.arange(c0, c0 + n)
+        else:
+            r, c = rng.permutation(nrows)[:m] + 1, rng.permutation(ncols)[:n] + 1
+        b = rng.standard_normal((m, n))
+        if np.dtype(dtype).kind == "c":
+            b = b + 1j * rng.standard_normal((m, n))
+        blocks.append(np.asfortranarray(b.astype(dtype)))
+        rows.append(r.astype(np.int64))
+        cols.append(c.astype(np.int64))
+    battery(B.BlockSparseMatrix(blocks, rows, cols, (nrows, ncols)), reps=1)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fuzz_symmetric(seed):
+    rng = np.random.default_rng(200 + seed)
+    dtype = [np.complex128, np.float64][seed % 2]
+    n = int(rng.integers(1500, 3000))
+    A = G.symmetric_nearfield(seed=300 + seed, n=n, leaf_min=5, leaf_max=320, k_near=int(rng.integers(1, 5)),
+                              dtype=dtype, permuted=bool(seed & 1))
+    for variant in (L.VARIANT_FUSED_TMA, L.VARIANT_FUSED, L.VARIANT_GATHER, L.VARIANT_COLOR):
+        A.device().set_variant(variant)
+        battery(A, reps=1)
+    A.device().set_variant(L.VARIANT_AUTO)
+    V = B.VariableBlockCompressedRowStorage(G.symmetric_nearfield(seed=300 + seed, n=n, leaf_min=5, leaf_max=320,
+                                                                  k_near=2, dtype=dtype)) if not (seed & 1) else None
+    if V is not None:                                    # the same structure through the VBCRS conversion
+        battery(V, reps=1)

@@ -329,3 +329,87 @@ def test_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared == {n for n, _, _ in L.SIGNATURES}
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_structures_all_plans_and_slabs(seed):
+    """Seeded fuzz of the packer: random block sizes (1..90 rows/cols, so segments land in every kernel class),
+    contiguous or arbitrary index vectors, overlaps, all three ops, every plan family (stream / gather / colour
+    where it exists) and a 3-way slab split with the local/remote phase partition — all replayed by the plan
+    interpreter against the oracle."""
+    rng = np.random.default_rng(100 + seed)
+    dtype = [np.float64, np.complex128, np.float32][seed % 3]
+    contiguous = seed % 2 == 0
+    nrows, ncols = int(rng.integers(150, 400)), int(rng.integers(150, 400))
+    blocks, rows, cols = [], [], []
+    for _ in range(int(rng.integers(20, 60))):
+        m, n = int(rng.integers(1, 91)), int(rng.integers(1, 91))
+        m, n = min(m, nrows), min(n, ncols)
+        if contiguous:
+            r0, c0 = int(rng.integers(1, nrows - m + 2)), int(rng.integers(1, ncols - n + 2))
+            r, c = np.arange(r0, r0 + m), np.arange(c0, c0 + n)
+        else:
+            r, c = rng.permutation(nrows)[:m] + 1, rng.permutation(ncols)[:n] + 1    # no repeats inside a block
+        b = rng.standard_normal((m, n))
+        if np.dtype(dtype).kind == "c":
+            b = b + 1j * rng.standard_normal((m, n))
+        blocks.append(np.asfortranarray(b.astype(dtype)))
+        rows.append(r.astype(np.int64))
+        cols.append(c.astype(np.int64))
+    A = O.OBSM(blocks, rows, cols, (nrows, ncols))
+    P = B.BlockSparseMatrix(blocks, rows, cols, (nrows, ncols))
+    D = host_only(P)
+    tol = 1e-4 if dtype == np.float32 else 1e-12
+    up = np.complex128 if np.dtype(dtype).kind == "c" else np.float64
+    has_color = D.table(L.TAB_COLOR_PTR, 4).size > 0
+    for op in OPS:
+        nin, nout = (ncols, nrows) if op == "N" else (nrows, ncols)
+        x = rng.standard_normal(nin).astype(dtype)
+        y0 = rng.standard_normal(nout).astype(dtype)
+        ref = O.mul_bsm(A, x.astype(up), op)
+        ref5 = O.mul_bsm(A, x.astype(up), op, 0.5, -1.5, False, y0.astype(up))
+        for variant in ("auto", "gather") + (("color",) if has_color else ()):
+            assert rel(run_plan(P, D, op, x, variant=variant), ref) < tol, (op, variant)
+            assert rel(run_plan(P, D, op, x, 0.5, -1.5, False, y0.copy(), variant=variant), ref5) < tol, (op, variant)
+    if nrows == ncols or True:
+        # slabs over the OUTPUT dimension of op N (rows); x ownership follows the column cuts of the same fractions
+        cuts_r = [0, nrows // 3, 2 * nrows // 3, nrows]
+        cuts_c = [0, ncols // 3, 2 * ncols // 3, ncols]
+        x = rng.standard_normal(ncols).astype(dtype)
+        y = np.zeros(nrows, up)
+        for k in range(3):
+            Ds = host_only(P, own_rows=(cuts_r[k], cuts_r[k + 1]), own_cols=(cuts_c[k], cuts_c[k + 1]))
+            run_plan(P, Ds, "N", x.astype(up), y=y, own=(cuts_r[k], cuts_r[k + 1]), in_own=(cuts_c[k], cuts_c[k + 1]))
+        assert rel(y, O.mul_bsm(A, x.astype(up), "N")) < tol
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_symmetric_structures(seed):
+    """Seeded fuzz of the symmetric path: leaf sizes from 5 to 320 rows (warp-eligible, CTA-kernel and taller-than-256
+    leaves in one matrix), contiguous or renumbered unknowns, all ops, stream / gather / colour plans, 2-way slabs."""
+    from bsm_b200 import generators as G
+    rng = np.random.default_rng(200 + seed)
+    dtype = [np.complex128, np.float64][seed % 2]
+    n = int(rng.integers(1500, 3000))
+    A = G.symmetric_nearfield(seed=300 + seed, n=n, leaf_min=5, leaf_max=320, k_near=int(rng.integers(1, 5)),
+                              dtype=dtype, permuted=bool(seed & 1))
+    OA = O.OSBM(A.diagonals, A.diagonalindices, A.offdiagonals, A.rowindices, A.colindices, A.size)
+    D = host_only(A)
+    x = rng.standard_normal(n).astype(dtype)
+    y0 = rng.standard_normal(n).astype(dtype)
+    if np.dtype(dtype).kind == "c":
+        x = x + 1j * rng.standard_normal(n)
+    for op in OPS:
+        ref = O.mul_sbm(OA, x, op)
+        for variant in ("fused", "gather", "color"):
+            assert rel(run_plan(A, D, op, x, variant=variant), ref) < 1e-12, (op, variant)
+        assert rel(run_plan(A, D, op, x, 0.7, -0.4, False, y0.copy()), O.mul_sbm(OA, x, op, 0.7, -0.4, False, y0.copy())) < 1e-12
+    if not (seed & 1):
+        from bsm_b200.partition import extract_slab, slab_cuts
+        cuts = slab_cuts(A, 2)
+        y = np.zeros(n, np.result_type(dtype, np.float64))
+        for k in range(2):
+            lo, hi = int(cuts[k]), int(cuts[k + 1])
+            S = extract_slab(A, lo, hi, ("N",))
+            run_plan(S, host_only(S, own_rows=(lo, hi), own_cols=(lo, hi)), "N", x, y=y, own=(lo, hi), in_own=(lo, hi))
+        assert rel(y, O.mul_sbm(OA, x, "N")) < 1e-12
