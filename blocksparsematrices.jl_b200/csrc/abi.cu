@@ -340,7 +340,8 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
     if (phase != 0 && (nrhs != 1 || p >= 4 || !scratch_io)) return fail(BSM_ERR_ARG, "phased multiply needs nrhs = 1");
     const int32_t nfused = (int32_t)HP.n_fused_slices;
     const int32_t nwarp = (int32_t)HP.n_warp_slices;
-    const bool use_tma = A->variant != BSM_VARIANT_FUSED;
+    // the direct-load comparison kernel only knows whole segments with short T-form blocks
+    const bool use_tma = A->variant != BSM_VARIANT_FUSED || HP.fused_general;
     if (nfused > 0 || nwarp > 0) {
         static bool attr_done_dev[64][3] = {};
         const int di = sizeof(T) == 4 ? 0 : sizeof(T) == 8 ? 1 : 2;

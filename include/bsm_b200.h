@@ -60,8 +60,8 @@ typedef enum {
     BSM_VARIANT_AUTO = 0,
     BSM_VARIANT_GATHER = 1,  /* owner-computes gather GEMV, direct global loads (two passes over
                                 half-stored symmetric blocks) */
-    BSM_VARIANT_FUSED = 2,   /* symmetric: one pass over each half-stored block, transposed partials
-                                gathered through the transposed index */
+    BSM_VARIANT_FUSED = 2,   /* comparison: the stream plan with DIRECT global loads in the CTA kernel (no TMA); plans
+                                with column sub-range slices or tall T-form blocks still use the TMA kernel */
     BSM_VARIANT_COLOR = 3,   /* colour-ordered multi-launch (the reference's schedule, for comparison):
                                 y <- beta*y, then per sweep one launch per colour of a greedy colouring of the
                                 "blocks share an output row" graph, each block accumulating straight into y */
