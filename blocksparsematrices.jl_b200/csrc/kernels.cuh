@@ -482,6 +482,9 @@ template <class T, int RPL, bool CONJ>
 __device__ __forceinline__ void consume_chunk(const T *__restrict__ sm, int32_t m, int32_t ncols, int lane,
                                               int warp, bool doN, bool doT, const T *__restrict__ xcol,
                                               const T *__restrict__ xrow, T (&accN)[RPL], T *tglobal, T *tsmem) {
+    // `warp` arrives already rotated by the number of column pairs consumed so far (see tma_consumer): with
+    // tall blocks a chunk holds fewer pairs than there are warps, and without the rotation warps 0..k would do
+    // all the work of every chunk while the others idle
     for (int32_t jc = 2 * warp; jc < ncols; jc += 2 * kFWarps) {
         const bool hasB = (jc + 1) < ncols;
         const T *cA = sm + jc * m;
@@ -585,6 +588,7 @@ __device__ __forceinline__ void tma_consumer(const MulArgs<T> &a, const bsm_slic
 #pragma unroll
     for (int k = 0; k < RPL; ++k) accN[k] = El<T>::zero();
     uint32_t q = 0;
+    uint32_t pbase = 0;   // column pairs consumed so far: rotates the pair -> warp assignment from chunk to chunk
     for (int32_t ci = sl.c_begin; ci < sl.c_end; ++ci) {
         const bsm_contrib cb = a.contrib[ci];
         const SetRef in = set_ref(a, cb.in_set);
@@ -620,11 +624,12 @@ __device__ __forceinline__ void tma_consumer(const MulArgs<T> &a, const bsm_slic
                 if (GEN && tall)
                     consume_chunk_tall<T, CONJ>(sm, m, ncols, j0, lane, warp, xs, accT + (j0 - r0));
                 else if (tform)
-                    consume_chunk<T, RPL, CONJ>(sm, m, ncols, lane, warp, false, true, nullptr, xs, accN, nullptr,
-                                                accT + (j0 - r0));
+                    consume_chunk<T, RPL, CONJ>(sm, m, ncols, lane, (warp - pbase) & (kFWarps - 1), false, true, nullptr, xs,
+                                                accN, nullptr, accT + (j0 - r0));
                 else
-                    consume_chunk<T, RPL, CONJ>(sm, m, ncols, lane, warp, true, fusedT, xs + (j0 - jw), xrs, accN,
-                                                fusedT ? tg + j0 : nullptr, nullptr);
+                    consume_chunk<T, RPL, CONJ>(sm, m, ncols, lane, (warp - pbase) & (kFWarps - 1), true, fusedT,
+                                                xs + (j0 - jw), xrs, accN, fusedT ? tg + j0 : nullptr, nullptr);
+                pbase += (uint32_t)((ncols + 1) >> 1);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
             }
