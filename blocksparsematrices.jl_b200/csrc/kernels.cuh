@@ -742,14 +742,16 @@ static_assert(kPStages * kPStageBytes >= kFWarps * kFMaxRows * 16, "reduction bu
 //                    completing on the SAME mbarrier (cp.async.mbarrier.arrive.noinc)
 //   * descriptors    bsm_wchunk records, bulk-copied in batches of 8 into a 32-entry descriptor ring
 // The ring placement (smem16) and the issue condition (lag) of every chunk are precomputed by the
-// packer — the chunk sequence of a work item is static — so up to ~20 KB per warp (8 warps per SM) are
-// in flight regardless of the block sizes. Lanes own rows (lane, lane+32):
+// packer — the chunk sequence of a work item is static — so ~7 KB per warp x 16 warps per SM are in flight
+// regardless of the block sizes (measured on C3: 8 warps x 24 KB rings 0.85 of the copy peak, 12 x 16 KB 0.91,
+// 16 x 11 KB 0.96, 20 x 8.5 KB 0.79: per-warp instruction latency, not bytes in flight, is the limit).
+// Lanes own rows (lane, lane+32):
 //   N-form  acc[r] += B[r, j] * x[j]           x[j] broadcast from shared memory
 //   T-form  t[j]   += sum_r B[r, j] * x[r]     four columns at a time, reduced by a halving butterfly
 //                                              (6 shuffles per 4 columns instead of 20)
 // At the last chunk of a segment the warp writes y (alpha/beta fused) or its partial vector.
 constexpr int kWWarps = 4;
-constexpr int kWRing = 16384;        // == plan.h kWRingBytes
+constexpr int kWRing = 11264;        // == plan.h kWRingBytes
 constexpr int kWNB = 16;             // == plan.h kWSlots
 constexpr int kWDBatch = 8;          // descriptors per bulk copy
 constexpr int kWDSlots = 4;          // descriptor ring = kWDSlots * kWDBatch records

@@ -38,7 +38,7 @@ constexpr int kFusedMaxRows = 256;
 constexpr int kFusedMaxTRows = 1024;    // tallest T-form block the CTA kernel stages (x window in shared memory)
 constexpr int kWarpMaxRows = 64;        // segment length and block height limit of the warp-stream kernel
 constexpr int kWChunkBytes = 4096;      // largest block payload of one warp-stream chunk
-constexpr int kWRingBytes = 16384;      // shared-memory byte ring of one warp (chunks + their x values)
+constexpr int kWRingBytes = 11264;      // shared-memory byte ring of one warp (chunks + their x values)
 constexpr int kWSlots = 16;             // mbarrier slots of one warp: chunks in flight + the one being consumed
 constexpr int kWMaxCols = 64;           // columns per warp-stream chunk (two prefetched x values per lane)
 // bsm_wchunk.flags

@@ -212,7 +212,7 @@ def run_warp_stream(D, plan, arena, S, slices, x_full, x_local, y, scratch, writ
         assert s["r0"] == 0 and s["r1"] == S.len[s["out_set"]] <= 64
 
 
-RING_BYTES, RING_SLOTS = 16384, 16
+RING_BYTES, RING_SLOTS = 11264, 16
 
 
 def check_ring_schedule(ch, isz):
