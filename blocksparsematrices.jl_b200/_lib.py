@@ -46,6 +46,7 @@ SIGNATURES = [
     ("bsm_create_vbcrs", c_int, [c_int, c_int64, c_int64, c_int64, c_int64, _P64, _P64, _P64,
                                  POINTER(c_void_p), _P64, _P64, POINTER(c_uint8), POINTER(Options),
                                  POINTER(c_void_p)]),
+    ("bsm_update_values", c_int, [c_void_p, POINTER(c_void_p), c_int64]),
     ("bsm_destroy", c_int, [c_void_p]),
     ("bsm_mul", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64,
                         c_int64, c_void_p]),
@@ -65,6 +66,9 @@ SIGNATURES = [
     ("bsm_plan_stats", c_int, [c_void_p, c_int, _P64]),
     ("bsm_table_count", c_int64, [c_void_p, c_int, c_int]),
     ("bsm_table_copy", c_int, [c_void_p, c_int, c_int, c_void_p, c_int64]),
+    ("bsm_sparse_build", c_int, [c_void_p, c_int, _P64]),
+    ("bsm_sparse_fetch", c_int, [c_void_p, _P64, _P64, c_void_p]),
+    ("bsm_sparse_device_pointers", c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), _P64]),
     ("bsm_dist_unique_id", c_int, [c_void_p]),
     ("bsm_dist_init", c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),
     ("bsm_dist_destroy", c_int, [c_void_p]),

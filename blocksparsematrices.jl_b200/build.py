@@ -13,14 +13,14 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libbsm_b200.so"
-SOURCES = ["abi.cu", "dist.cu", "pack.cpp"]
+SOURCES = ["abi.cu", "dist.cu", "sparse.cu", "pack.cpp"]
 DEPS = ["kernels.cuh", "spmm.cuh", "plan.h", "../../include/bsm_b200.h"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
-    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-pthread",
     "-shared",
     "-ldl",
 ]

@@ -10,6 +10,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -100,6 +101,9 @@ struct bsm_matrix {
     void *hx = nullptr, *hy = nullptr;
     int64_t hx_bytes = 0, hy_bytes = 0;
     cudaStream_t host_stream = nullptr;
+    // sparse(A) result built by bsm_sparse_build (sparse.cu), device arrays
+    void *sparse_slot[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool restricted = false;
     // benchmarking: events around the kernels of the last bsm_mul
     bool profiling = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -140,8 +144,10 @@ int resolve_device(const bsm_options *opt, int *dev) {
 int upload_arena(bsm_matrix *A) {
     HostMatrix &H = A->H;
     const int64_t s = dtype_size(H.dtype);
-    CUDA_TRY(cudaMalloc(&A->arena, (size_t)H.arena_elems * s));
-    CUDA_TRY(cudaMemset(A->arena, 0, (size_t)H.arena_elems * s));
+    if (!A->arena) {   // first upload (bsm_update_values reuses the arena: padding stays zero)
+        CUDA_TRY(cudaMalloc(&A->arena, (size_t)H.arena_elems * s));
+        CUDA_TRY(cudaMemset(A->arena, 0, (size_t)H.arena_elems * s));
+    }
     const int64_t stage_bytes = 64ll << 20;
     unsigned char *stage[2] = {nullptr, nullptr};
     cudaEvent_t done[2];
@@ -154,8 +160,51 @@ int upload_arena(bsm_matrix *A) {
     int cur = 0;
     int64_t fill = 0;        // bytes used in stage[cur]
     int64_t dst_off = -1;    // arena byte offset the staged run starts at
+    // Host blocks are separate heap allocations (Julia `Vector{Matrix{T}}`): filling a pinned staging buffer is a
+    // gather of many memcpys, which one thread cannot feed at PCIe speed. The copies of one staging buffer are
+    // recorded as jobs (large ones cut into 1 MB pieces) and executed by a few threads while the previous buffer
+    // is in flight.
+    struct Job {
+        unsigned char *dst;
+        const unsigned char *src;
+        int64_t bytes;      // plain copy when m == 0
+        int64_t e0;         // transposed block: first arena element of the piece
+        int32_t m, n;
+    };
+    std::vector<Job> jobs;
+    const unsigned nthreads = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    auto run_jobs = [&]() {
+        if (jobs.empty()) return;
+        auto work = [&](unsigned t) {
+            for (size_t k = t; k < jobs.size(); k += nthreads) {
+                const Job &j = jobs[k];
+                if (j.m == 0) {
+                    std::memcpy(j.dst, j.src, (size_t)j.bytes);
+                } else {
+                    // arena block is m x n (ld m); host parent is n x m (ld n): A[i,j] = Parent[j,i]
+                    const int64_t cnt = j.bytes / s;
+                    for (int64_t e = 0; e < cnt; ++e) {
+                        const int64_t i = (j.e0 + e) % j.m, c = (j.e0 + e) / j.m;
+                        std::memcpy(j.dst + e * s, j.src + (i * j.n + c) * s, (size_t)s);
+                    }
+                }
+            }
+        };
+        int64_t total = 0;
+        for (const Job &j : jobs) total += j.bytes;
+        if (nthreads == 1 || total < (4 << 20)) {
+            for (unsigned t = 0; t < nthreads; ++t) work(t);
+        } else {
+            std::vector<std::thread> pool;
+            for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+            work(0);
+            for (auto &th : pool) th.join();
+        }
+        jobs.clear();
+    };
     auto flush = [&]() -> int {
         if (fill == 0) return 0;
+        run_jobs();
         CUDA_TRY(cudaMemcpyAsync((unsigned char *)A->arena + dst_off, stage[cur], (size_t)fill,
                                  cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaEventRecord(done[cur], st));
@@ -165,6 +214,7 @@ int upload_arena(bsm_matrix *A) {
         dst_off = -1;
         return 0;
     };
+    const int64_t piece = 1 << 20;
     for (size_t b = 0; b < H.blocks.size(); ++b) {
         const BlockSrc &src = H.blocks[b];
         const int64_t bytes = (int64_t)src.m * src.n * s;
@@ -183,18 +233,21 @@ int upload_arena(bsm_matrix *A) {
                 }
             }
             if (fill == 0) dst_off = boff + done_b;
-            const int64_t take = std::min(bytes - done_b, stage_bytes - fill);
+            const int64_t take = std::min(std::min(bytes - done_b, stage_bytes - fill), piece);
+            Job j;
+            j.dst = stage[cur] + fill;
+            j.bytes = take;
             if (!src.transposed) {
-                std::memcpy(stage[cur] + fill, (const unsigned char *)src.host + done_b, (size_t)take);
+                j.src = (const unsigned char *)src.host + done_b;
+                j.e0 = 0;
+                j.m = j.n = 0;
             } else {
-                // arena block is m x n (ld m); host parent is n x m (ld n): A[i,j] = Parent[j,i]
-                const int64_t e0 = done_b / s, e1 = (done_b + take) / s;
-                for (int64_t e = e0; e < e1; ++e) {
-                    const int64_t i = e % src.m, j = e / src.m;
-                    std::memcpy(stage[cur] + fill + (e - e0) * s,
-                                (const unsigned char *)src.host + (i * src.n + j) * s, (size_t)s);
-                }
+                j.src = (const unsigned char *)src.host;
+                j.e0 = done_b / s;
+                j.m = src.m;
+                j.n = src.n;
             }
+            jobs.push_back(j);
             fill += take;
             done_b += take;
             if (fill == stage_bytes)
@@ -257,6 +310,7 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
         pp[1].in_lo = opt->own_row_lo;
         pp[1].in_hi = opt->own_row_hi;
         A->variant = opt->variant;
+        A->restricted = opt->own_row_hi >= 0 || opt->own_col_hi >= 0;
     }
     // work-item budget of the stream plans: no CTA should hold more than ~1/8 of a resident slot's fair share (LPT tail <= ~6 %)
     const int64_t total_bytes = [&] {
@@ -799,6 +853,23 @@ int bsm_create_vbcrs(int dtype, int64_t nrows, int64_t ncols, int64_t nbrows, in
     return finish_create(A, ir, opt, out);
 }
 
+int bsm_update_values(bsm_handle h, const void *const *blocks, int64_t nb) {
+    if (int rc = check_handle(h)) return rc;
+    if (h->device == BSM_DEVICE_NONE) return fail(BSM_ERR_CUDA, "host-only handle has no arena");
+    if (nb != (int64_t)h->H.blocks.size()) return fail(BSM_ERR_ARG, "block count differs from the handle's");
+    if (nb > 0 && !blocks) return fail(BSM_ERR_ARG, "blocks is null");
+    for (int64_t b = 0; b < nb; ++b) {
+        if (!blocks[b] && (int64_t)h->H.blocks[b].m * h->H.blocks[b].n > 0) return fail(BSM_ERR_ARG, "null block");
+        h->H.blocks[b].host = blocks[b];
+    }
+    DeviceGuard g(h->device);
+    if (!g.ok) return fail(BSM_ERR_CUDA, "cudaSetDevice failed");
+    CUDA_TRY(cudaDeviceSynchronize());   // no multiply may still be reading the arena
+    const int rc = upload_arena(h);
+    for (auto &b : h->H.blocks) b.host = nullptr;
+    return rc;
+}
+
 int bsm_destroy(bsm_handle h) {
     if (!h) return 0;
     if (h->device == BSM_DEVICE_NONE) {
@@ -807,6 +878,12 @@ int bsm_destroy(bsm_handle h) {
     }
     DeviceGuard g(h->device);
     if (h->arena) cudaFree(h->arena);
+    if (h->sparse_slot[7]) {
+        SparseResult *R = reinterpret_cast<SparseResult *>(h->sparse_slot);
+        if (R->colptr) cudaFree(R->colptr);
+        if (R->rowval) cudaFree(R->rowval);
+        if (R->nzval) cudaFree(R->nzval);
+    }
     h->set_len.release();
     h->set_start.release();
     h->set_pool_off.release();
@@ -891,6 +968,28 @@ int bsm_plan_has_remote(bsm_handle h, int op) {
     const int p = plan_index(h, op);
     return (p < 4 && h->H.plan[p].has_remote) ? 1 : 0;
 }
+// ---- sparse.cu hooks
+static_assert(sizeof(SparseResult) <= sizeof(void *) * 8, "sparse slot too small");
+int bsm_sparse_source(bsm_handle h, SparseSource *out) {
+    if (h->device == BSM_DEVICE_NONE) return fail(BSM_ERR_CUDA, "host-only handle: no device, and there is no CPU fallback");
+    out->H = &h->H;
+    out->arena = h->arena;
+    out->set_start = h->set_start.p;
+    out->set_pool_off = h->set_pool_off.p;
+    out->pool = h->pool.p;
+    out->device = h->device;
+    out->restricted = h->restricted;
+    return 0;
+}
+SparseResult *bsm_sparse_slot(bsm_handle h) {
+    SparseResult *R = reinterpret_cast<SparseResult *>(h->sparse_slot);
+    if (!h->sparse_slot[7]) {     // first use: construct in place (slot 7 doubles as the "initialised" mark)
+        new (R) SparseResult();
+        h->sparse_slot[7] = (void *)1;
+    }
+    return R;
+}
+
 int64_t bsm_plan_scratch_bytes(bsm_handle h, int op) {
     if (!h || op < BSM_OP_N || op > BSM_OP_C) return 0;
     return h->H.plan[plan_index(h, op)].scratch_elems * (int64_t)dtype_size(h->H.dtype);

@@ -167,6 +167,22 @@ void layout_arena(HostMatrix &M);
 std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t out_dim,
                        int64_t in_dim, const PlanParams &pp, HostPlan &P);
 
+// ---- sparse.cu <-> abi.cu (the handle's internals stay in abi.cu) --------------------------------------
+struct SparseSource {
+    const HostMatrix *H;
+    const void *arena;
+    const int32_t *set_start;
+    const int64_t *set_pool_off;
+    const int32_t *pool;
+    int device;
+    bool restricted;
+};
+struct SparseResult {     // device arrays of the last bsm_sparse_build: int64 colptr / rowval (1-based), T nzval
+    int64_t nnz = -1, ncols = 0;
+    int dtype = 0;
+    void *colptr = nullptr, *rowval = nullptr, *nzval = nullptr;
+};
+
 // Colour-ordered plan: the reference's schedule (/root/reference/src/coloring.jl:20-61 builds the conflict
 // graph "two blocks share an output row" and colours it; src/blockmatrix.jl:231-244 runs colour by
 // colour). Greedy first-fit colouring per sweep stands in for GraphsColoring (it only changes the grouping,

@@ -114,6 +114,33 @@ class DeviceMatrix:
         self._h = h
         self.device = device
 
+    def sparse(self, op="N"):
+        """SparseArrays.sparse(op(A)) built on the device (bsm_sparse_build / _fetch) -> scipy CSC in Julia's
+        canonical form (sorted rows, duplicates summed, explicit zeros kept)."""
+        import scipy.sparse as sp
+        nnz = c_int64(0)
+        L.check(L.lib().bsm_sparse_build(self._h, _OPS[op], byref(nnz)))
+        nc = self.size[1] if op == "N" else self.size[0]
+        nr = self.size[0] if op == "N" else self.size[1]
+        colptr = np.zeros(nc + 1, np.int64)
+        rowval = np.zeros(nnz.value, np.int64)
+        nzval = np.zeros(nnz.value, self.dtype)
+        L.check(L.lib().bsm_sparse_fetch(self._h, _i64p(colptr), _i64p(rowval), nzval.ctypes.data_as(c_void_p)))
+        return sp.csc_matrix((nzval, rowval - 1, colptr - 1), shape=(nr, nc))
+
+    def update_values(self, A):
+        """Re-uploads the block values of `A` (same structure as the matrix this handle was built from) into the
+        arena, without re-planning."""
+        if isinstance(A, SymmetricBlockMatrix):
+            blocks = list(A.diagonals) + list(A.offdiagonals)
+            allow_tr = False
+        else:
+            blocks = list(A.blocks)
+            allow_tr = isinstance(A, VariableBlockCompressedRowStorage)
+        keep, ptrs, m, n, tr = _colmajor(blocks, self.dtype, allow_transposed=allow_tr)
+        L.check(L.lib().bsm_update_values(self._h, ptrs.ctypes.data_as(POINTER(c_void_p)), len(blocks)))
+        self.host = A
+
     # ---- lifetime
     def close(self):
         if getattr(self, "_h", None):

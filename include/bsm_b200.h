@@ -12,6 +12,7 @@
  *                            src/symmetricblockmatrix.jl:386-435, src/vbcrs.jl:266-288, 303-354
  *   bsm_mul_host             the same call with HOST x / y (copies inside) — what `mul!(y, A, x)` on
  *                            Julia Arrays maps to when the caller holds no device arrays
+ *   bsm_update_values        the same constructors when only the block values changed (no re-planning)
  *   bsm_nnz                  SparseArrays.nnz                         src/blockmatrix.jl:208-223,
  *                            src/symmetricblockmatrix.jl:367-384, src/vbcrs.jl:290-296
  *   bsm_size                 Base.size                                src/abstractblockmatrix.jl:23-25
@@ -115,6 +116,12 @@ int bsm_create_vbcrs(int dtype, int64_t nrows, int64_t ncols, int64_t nbrows, in
                      const int64_t *rowptr, const int64_t *colstart, const int64_t *rowstart,
                      const void *const *blocks, const int64_t *m, const int64_t *n,
                      const uint8_t *is_transposed, const bsm_options *opt, bsm_handle *out);
+
+/* New VALUES, same structure (a BEM matrix re-assembled for another frequency, a time step, ...): re-uploads
+ * the blocks into the existing arena without re-planning. `blocks` holds nb host pointers in creation order
+ * (symmetric: the diagonal blocks, then the off-diagonal blocks), each of the shape (and, for VBCRS, the
+ * is_transposed flag) given at creation. Synchronises the device first. */
+int bsm_update_values(bsm_handle h, const void *const *blocks, int64_t nb);
 
 int bsm_destroy(bsm_handle h);
 
@@ -238,6 +245,16 @@ typedef struct {
 
 int64_t bsm_table_count(bsm_handle h, int table, int plan); /* number of elements/records, <0 on error */
 int bsm_table_copy(bsm_handle h, int table, int plan, void *dst, int64_t dst_bytes);
+
+/* ---- sparse(A) on the device ---------------------------------------------------
+ * SparseArrays.sparse(op(A)) (src/sparse.jl:17-129) built from the resident arena: canonical CSC — columns in
+ * order, rows sorted inside a column, duplicates (overlapping blocks) summed, explicit zeros kept — with
+ * 1-based Int64 colptr / rowval exactly as a Julia SparseMatrixCSC holds them. bsm_sparse_build leaves the
+ * three arrays on the device (bsm_sparse_device_pointers, e.g. for cuSPARSE); bsm_sparse_fetch copies them to
+ * host arrays of ncols+1, nnz and nnz elements and releases the device copy. Not available on slab handles. */
+int bsm_sparse_build(bsm_handle h, int op, int64_t *nnz_out);
+int bsm_sparse_fetch(bsm_handle h, int64_t *colptr, int64_t *rowval, void *nzval);
+int bsm_sparse_device_pointers(bsm_handle h, void **colptr_dev, void **rowval_dev, void **nzval_dev, int64_t *nnz);
 
 /* ---- single-box multi-GPU: block-row slabs + NCCL all-gather of x ------------------
  * One process per GPU. Rank r builds its handle from the blocks of its slab with

@@ -358,3 +358,67 @@ def test_fuzz_symmetric(seed):
                                                                   k_near=2, dtype=dtype)) if not (seed & 1) else None
     if V is not None:                                    # the same structure through the VBCRS conversion
         battery(V, reps=1)
+
+
+def test_update_values_keeps_the_plan():
+    """bsm_update_values: new block values in the existing arena, no re-planning (structure unchanged)."""
+    A = G.symmetric_nearfield(seed=61, n=8000, k_near=3)
+    A2 = G.symmetric_nearfield(seed=62, n=8000, k_near=3)          # same structure generator parameters, other values
+    assert [b.shape for b in A.offdiagonals] != [] and len(A.offdiagonals) != 0
+    # same structure: only valid when the shapes agree; build the second matrix on the first one's structure
+    A2 = B.SymmetricBlockMatrix([2.0 * d for d in A.diagonals], A.diagonalindices,
+                                [np.asfortranarray(-1.5 * o) for o in A.offdiagonals], A.rowindices, A.colindices, A.size)
+    D = A.device()
+    x = randx(np.random.default_rng(3), 8000, np.complex128)
+    y1 = D.mul("N", x)
+    assert rel2(y1, oracle_mul(A, x, "N")) < 1e-12
+    D.update_values(A2)
+    assert rel2(D.mul("N", x), oracle_mul(A2, x, "N")) < 1e-12
+    assert rel2(D.mul("C", x), oracle_mul(A2, x, "C")) < 1e-12
+    with pytest.raises(L.BsmError):
+        L.check(L.lib().bsm_update_values(D._h, None, 3))
+
+
+# ---- sparse(A) on the device vs the host restatement of src/sparse.jl -------------------------------------------
+def sparse_check(A, exact_values=True):
+    D = A.device()
+    for op in OPS:
+        S = D.sparse(op)
+        if isinstance(A, B.VariableBlockCompressedRowStorage) and op != "N":
+            # the reference defines rowcolvals only for the unwrapped VBCRS: compare with sparse(A)^T / sparse(A)'
+            Hs = B.sparse(A).T.tocsc() if op == "T" else B.sparse(A).conj().T.tocsc()
+            Hs.sort_indices()
+        else:
+            Hs = B.sparse(wrap(A, op))                  # host: rowcolvals + canonical CSC (scipy)
+        assert S.shape == Hs.shape and S.nnz == Hs.nnz == (B.nnz(A) if exact_values else Hs.nnz)
+        assert np.array_equal(S.indptr, Hs.indptr) and np.array_equal(S.indices, Hs.indices)   # structure bit-exact
+        if exact_values:
+            assert np.array_equal(S.data, Hs.data)      # no duplicates: values are copies (conj for op C)
+        else:
+            assert np.max(np.abs(S.data - Hs.data)) <= 1e-13 * max(1.0, np.max(np.abs(Hs.data)))
+
+
+def test_sparse_on_device(golden):
+    A = B.SymmetricBlockMatrix(golden.diagonals, golden.diagonalindices, golden.offdiagonals,
+                               golden.rowindices, golden.colindices, golden.size)
+    sparse_check(A)
+    S = A.device().sparse("N")
+    assert abs(S - S.T).nnz == 0                                     # issymmetric (test_symmetricblockmatrix.jl:49)
+    E = O.sbm_to_bsm(golden)
+    sparse_check(B.BlockSparseMatrix(E.blocks, E.rowindices, E.colindices, E.size))
+
+
+def test_sparse_on_device_other_types():
+    sparse_check(G.vbcrs_variable(seed=71, n=20000))
+    sparse_check(G.blocksparse_uniform(seed=72, n=3200, nblocks=400, bs=32, dtype=np.float32, permuted=True))
+    # overlapping blocks: duplicates are summed (values to rounding, structure exact); explicit zeros are kept
+    from test_packing_cpu import random_bsm
+    rng = np.random.default_rng(73)
+    blocks, rows, cols = random_bsm(rng, 60, 50, 40, np.float64, contiguous=True, maxdim=12)
+    blocks[0][:] = 0.0
+    Ab = B.BlockSparseMatrix(blocks, rows, cols, (60, 50))
+    sparse_check(Ab, exact_values=False)
+    assert (Ab.device().sparse("N").data == 0).sum() > 0
+    # empty matrix
+    Es = B.BlockSparseMatrix([], [], [], (7, 5)).device().sparse("N")
+    assert Es.shape == (7, 5) and Es.nnz == 0
