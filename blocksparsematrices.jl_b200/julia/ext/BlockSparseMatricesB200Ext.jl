@@ -122,4 +122,29 @@ function LinearMaps._unsafe_mul!(y::AbstractVecOrMat{T}, A::B200Map{T}, x::Abstr
     return LinearMaps._unsafe_mul!(y, A, convert(Array{T}, x), α, β)
 end
 
+# SparseArrays.sparse(A) built on the device from the resident arena (src/sparse.jl:127-129): canonical CSC,
+# 1-based Int64 colptr / rowval exactly as SparseMatrixCSC holds them.
+function SparseArrays.sparse(A::B200Map{T}) where {T}
+    P = parentmap(A)
+    nnzref = Ref{Int64}(0)
+    check(ccall((:bsm_sparse_build, libbsm_b200), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}), P.handle, opcode(A), nnzref))
+    m, n = size(A)
+    colptr = Vector{Int64}(undef, n + 1); rowval = Vector{Int64}(undef, nnzref[]); nzval = Vector{T}(undef, nnzref[])
+    check(ccall((:bsm_sparse_fetch, libbsm_b200), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{T}),
+                P.handle, colptr, rowval, nzval))
+    return SparseMatrixCSC(m, n, colptr, rowval, nzval)
+end
+
+# new values, same structure: re-upload without re-planning (blocks in creation order)
+function update!(B::B200Matrix{T}, blocks::Vector{<:AbstractMatrix}) where {T}
+    keep = [colmajor(T, b) for b in blocks]
+    ptrs = Ptr{Cvoid}[pointer(b) for b in keep]
+    GC.@preserve keep check(ccall((:bsm_update_values, libbsm_b200), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Int64),
+                                  B.handle, ptrs, length(ptrs)))
+    return B
+end
+
+# kernel variant for comparisons: 0 auto (stream), 1 gather, 2 direct loads, 3 colour-ordered (the reference's schedule)
+setvariant!(B::B200Matrix, v::Integer) = (check(ccall((:bsm_set_variant, libbsm_b200), Cint, (Ptr{Cvoid}, Cint), B.handle, v)); B)
+
 end # module
