@@ -258,6 +258,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--xchg", default="peer", choices=["peer", "nccl"],
+                    help="N > 1, one right-hand side: peer = x read from its owners over NVLink inside the kernels "
+                         "(no collective); nccl = all-gather of x, then multiply")
     ap.add_argument("--broadcasts", action="store_true", help="N > 1: grouped in-place broadcasts instead of the all-gather")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-gather, then multiply, on one stream")
     ap.add_argument("--op", default=None, choices=["N", "T", "C"], help="override the workload's op (development)")
@@ -335,7 +338,24 @@ def main():
         y_dev = torch.zeros((nrhs, nout), dtype=tdt, device=dev).t()
     x_full = x_host.to(dev) if nrhs == 1 else x_host.t().to(dev).t()
 
-    if world > 1:
+    peer = world > 1 and nrhs == 1 and args.xchg == "peer"
+    if peer:
+        try:
+            xs = comm.alloc(nin, np.dtype({"c128": np.complex128, "f64": np.float64, "f32": np.float32}[spec["dtype"]]))
+            xs.copy_(x_full)
+            ok = 1
+        except Exception as exc:       # no peer access between the GPUs of this box: NCCL path
+            print(f"[rank {rank}] peer mode unavailable ({exc}); falling back to the NCCL all-gather", file=sys.stderr)
+            ok = 0
+        t_ok = torch.tensor([ok], device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
+        peer = bool(t_ok.item())
+    if peer:
+        x_full = xs
+
+        def step():
+            SM.mul_peer(op, x_full, y_dev)   # bsm_mul_dist_peer: flag barrier, multiply reading x over NVLink, flag barrier
+    elif world > 1:
         def step():
             SM.mul(op, x_full, y_dev)   # bsm_mul_dist: NCCL all-gather of the x slabs (in place), then the slab multiply
     else:
@@ -495,8 +515,9 @@ def main():
                    if not l2_resident else "working set fits L2: L2 flushed (256 MB write) before every timed iteration, "
                                            "each multiply timed by its own CUDA events",
                    "variant": {0: "auto", 1: "gather", 2: "fused", 3: "color", 4: "fused_tma"}[args.variant],
-                   "parallelism": (f"block-row slabs x{world}, NCCL all-gather of x "
-                                   f"({'sequential' if args.no_overlap else 'overlapped with the rank-local slices'})")
+                   "parallelism": (f"block-row slabs x{world}, " +
+                                   ("x read from its owners' peer-mapped arrays over NVLink inside the kernels (no collective)"
+                                    if peer else f"NCCL all-gather of x ({'sequential' if args.no_overlap else 'overlapped with the rank-local slices'})"))
                    if world > 1 else "single GPU",
                    "algorithmic_bytes": work["bytes"], "flops": work["flops"],
                    "gen_s": round(t_gen, 1), "pack_s": round(t_pack, 1), "plan": stats},

@@ -77,6 +77,10 @@ SIGNATURES = [
     ("bsm_dist_info", c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     ("bsm_dist_allgather_rows", c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, _P64, c_void_p]),
     ("bsm_dist_allreduce_max_f64", c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    ("bsm_dist_alloc", c_int, [c_void_p, c_size_t, POINTER(c_void_p)]),
+    ("bsm_dist_free", c_int, [c_void_p, c_void_p]),
+    ("bsm_mul_dist_peer", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, _P64,
+                                  c_void_p]),
     ("bsm_mul_dist", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p,
                              c_int64, c_int64, _P64, c_void_p]),
     ("bsm_device_count", c_int, [POINTER(c_int)]),

@@ -386,12 +386,13 @@ int plan_index(const bsm_matrix *A, int op) {
 template <class T>
 int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int beta_is_false,
                const T *x, int64_t ldx, T *y, int64_t ldy, int64_t nrhs, cudaStream_t st, int phase = 0,
-               void **scratch_io = nullptr) {
+               void **scratch_io = nullptr, const PeerX *px = nullptr) {
     const int p = plan_index(A, op);
     const HostPlan &HP = A->H.plan[p];
     const DevPlan &DP = A->plan[p];
     T *scratch = nullptr;
     if (phase != 0 && (nrhs != 1 || p >= 4 || !scratch_io)) return fail(BSM_ERR_ARG, "phased multiply needs nrhs = 1");
+    if (px && px->npeer > 0 && (nrhs != 1 || p >= 4)) return fail(BSM_ERR_ARG, "peer-mode multiply needs nrhs = 1");
     const int32_t nfused = (int32_t)HP.n_fused_slices;
     const int32_t nwarp = (int32_t)HP.n_warp_slices;
     // the direct-load comparison kernel only knows whole segments with short T-form blocks
@@ -439,7 +440,8 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             a.set_start = A->set_start.p;
             a.set_pool_off = A->set_pool_off.p;
             a.pool = A->pool.p;
-            a.x = x + j * ldx;
+            a.x.x = x + j * ldx;
+            a.x.npeer = 0;
             a.y = y + j * ldy;
             a.scratch = nullptr;
             std::memcpy(&a.alpha, alpha, sizeof(T));
@@ -536,7 +538,13 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
         a.set_start = A->set_start.p;
         a.set_pool_off = A->set_pool_off.p;
         a.pool = A->pool.p;
-        a.x = x + j * ldx;
+        a.x.x = x + j * ldx;
+        a.x.npeer = 0;
+        if (px && px->npeer > 0) {   // peer mode (nrhs = 1): element i comes from its owner's array
+            a.x.npeer = px->npeer;
+            for (int r = 0; r < px->npeer; ++r) a.x.peer[r] = (const T *)px->peer[r];
+            for (int r = 0; r <= px->npeer; ++r) a.x.cuts[r] = px->cuts[r];
+        }
         a.y = y + j * ldy;
         a.scratch = scratch;
         std::memcpy(&a.alpha, alpha, sizeof(T));
@@ -995,7 +1003,7 @@ int64_t bsm_plan_scratch_bytes(bsm_handle h, int op) {
     return h->H.plan[plan_index(h, op)].scratch_elems * (int64_t)dtype_size(h->H.dtype);
 }
 int bsm_mul_phase(bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false, const void *x_dev,
-                  void *y_dev, void *stream, int phase, void **scratch_io) {
+                  void *y_dev, void *stream, int phase, void **scratch_io, const PeerX *px) {
     if (int rc = check_handle(h)) return rc;
     if (h->device == BSM_DEVICE_NONE) return fail(BSM_ERR_CUDA, "host-only handle");
     DeviceGuard g(h->device);
@@ -1003,13 +1011,13 @@ int bsm_mul_phase(bsm_handle h, int op, const void *alpha, const void *beta, int
     switch (h->H.dtype) {
     case BSM_F32:
         return launch_mul<float>(h, op, alpha, beta, beta_is_false, (const float *)x_dev, 0, (float *)y_dev, 0, 1, st,
-                                 phase, scratch_io);
+                                 phase, scratch_io, px);
     case BSM_F64:
         return launch_mul<double>(h, op, alpha, beta, beta_is_false, (const double *)x_dev, 0, (double *)y_dev, 0, 1,
-                                  st, phase, scratch_io);
+                                  st, phase, scratch_io, px);
     default:
         return launch_mul<cplx>(h, op, alpha, beta, beta_is_false, (const cplx *)x_dev, 0, (cplx *)y_dev, 0, 1, st,
-                                phase, scratch_io);
+                                phase, scratch_io, px);
     }
 }
 

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/bsm_b200.h"
+#include "plan.h"
 
 namespace {
 
@@ -80,7 +81,7 @@ void bsm_set_error(const std::string &msg);
 int bsm_plan_has_remote(bsm_handle h, int op);
 int64_t bsm_plan_scratch_bytes(bsm_handle h, int op);
 int bsm_mul_phase(bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false, const void *x_dev,
-                  void *y_dev, void *stream, int phase, void **scratch_io);
+                  void *y_dev, void *stream, int phase, void **scratch_io, const bsm::PeerX *px);
 
 struct bsm_comm_s {
     ncclComm_t comm = nullptr;
@@ -92,6 +93,16 @@ struct bsm_comm_s {
     int use_broadcasts = 0;                 // comparison: one grouped in-place broadcast per rank and column
     void *stage = nullptr;                  // nranks equal chunks of max-slab size for ncclAllGather
     size_t stage_bytes = 0;
+    // peer mode: allocations mapped into every rank (CUDA IPC), and the flag words of the two barriers that
+    // bracket a peer-mode multiply
+    struct Shared {
+        void *local = nullptr;
+        void *peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    };
+    std::vector<Shared> shared;
+    int32_t *flags = nullptr;               // this rank's flag array: ready[nranks], done[nranks]
+    int32_t **peer_flags_dev = nullptr;     // device array: every rank's flag array
+    int32_t epoch = 0;
 };
 
 namespace {
@@ -166,6 +177,12 @@ int bsm_dist_set_overlap(bsm_comm c, int on) {
 
 int bsm_dist_destroy(bsm_comm c) {
     if (!c) return 0;
+    for (auto &sh : c->shared) {
+        for (int p = 0; p < c->nranks; ++p)
+            if (p != c->rank && sh.peer[p]) cudaIpcCloseMemHandle(sh.peer[p]);
+        if (sh.local) cudaFree(sh.local);
+    }
+    if (c->peer_flags_dev) cudaFree(c->peer_flags_dev);
     if (c->stage) cudaFree(c->stage);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
@@ -212,7 +229,13 @@ int bsm_dist_allgather_rows(bsm_comm c, int dtype, void *x_dev, int64_t ldx, int
         const size_t chunk = (size_t)(maxrows * nrhs * s);
         const size_t need = chunk * (size_t)c->nranks;
         if (c->stage_bytes < need) {
-            if (c->stage) cudaFree(c->stage);
+            for (auto &sh : c->shared) {
+        for (int p = 0; p < c->nranks; ++p)
+            if (p != c->rank && sh.peer[p]) cudaIpcCloseMemHandle(sh.peer[p]);
+        if (sh.local) cudaFree(sh.local);
+    }
+    if (c->peer_flags_dev) cudaFree(c->peer_flags_dev);
+    if (c->stage) cudaFree(c->stage);
             c->stage = nullptr;
             c->stage_bytes = 0;
             if (cudaMalloc(&c->stage, need) != cudaSuccess) return dfail(BSM_ERR_ALLOC, "staging buffer of the all-gather");
@@ -258,6 +281,133 @@ int bsm_dist_set_collective(bsm_comm c, int use_broadcasts) {
     return 0;
 }
 
+// ---- peer mode: x is read straight from its owners over NVLink -------------------------------------------
+namespace {
+
+// every rank tells every peer "my part of epoch `epoch` is finished" (which = 0: my x slab is written,
+// which = 1: I have finished reading x)
+__global__ void flag_signal_kernel(int32_t *const *peer_flags, int which, int rank, int nranks, int32_t epoch) {
+    const int p = threadIdx.x;
+    if (p >= nranks) return;
+    __threadfence_system();
+    *reinterpret_cast<volatile int32_t *>(peer_flags[p] + which * nranks + rank) = epoch;
+    __threadfence_system();
+}
+// ... and waits until every peer has said so
+__global__ void flag_wait_kernel(const int32_t *flags, int which, int nranks, int32_t epoch) {
+    const int p = threadIdx.x;
+    if (p >= nranks) return;
+    const volatile int32_t *f = flags + which * nranks + p;
+    const long long t0 = clock64();
+    while (*f < epoch) {
+        __nanosleep(100);
+        if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s: a peer died or never entered the collective call
+    }
+    __threadfence_system();
+}
+
+// collective: cudaMalloc on every rank, IPC handles exchanged through the communicator, peers mapped
+int shared_alloc(bsm_comm c, size_t bytes, bsm_comm_s::Shared *out) {
+    if (c->nranks > 8) return dfail(BSM_ERR_UNSUPPORTED, "peer mode supports up to 8 ranks");
+    if (cudaSetDevice(c->device) != cudaSuccess) return dfail(BSM_ERR_CUDA, "cudaSetDevice failed");
+    bsm_comm_s::Shared sh;
+    if (cudaMalloc(&sh.local, bytes ? bytes : 16) != cudaSuccess) return dfail(BSM_ERR_ALLOC, "cudaMalloc of a peer-mapped array failed");
+    if (cudaMemset(sh.local, 0, bytes ? bytes : 16) != cudaSuccess) return dfail(BSM_ERR_CUDA, "cudaMemset failed");
+    sh.peer[c->rank] = sh.local;
+    if (c->nranks > 1) {
+        cudaIpcMemHandle_t mine;
+        if (cudaIpcGetMemHandle(&mine, sh.local) != cudaSuccess) return dfail(BSM_ERR_CUDA, "cudaIpcGetMemHandle failed");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        unsigned char *dbuf = nullptr;
+        if (cudaMalloc(&dbuf, 64 * (size_t)c->nranks) != cudaSuccess) return dfail(BSM_ERR_ALLOC, "cudaMalloc failed");
+        cudaMemcpy(dbuf + 64 * c->rank, &mine, 64, cudaMemcpyHostToDevice);
+        ncclResult_t r = nccl().AllGather(dbuf + 64 * c->rank, dbuf, 64, ncclChar, c->comm, c->comm_stream);
+        if (r != ncclSuccess || cudaStreamSynchronize(c->comm_stream) != cudaSuccess) {
+            cudaFree(dbuf);
+            return dfail(BSM_ERR_CUDA, "exchange of the IPC handles failed");
+        }
+        std::vector<cudaIpcMemHandle_t> all((size_t)c->nranks);
+        cudaMemcpy(all.data(), dbuf, 64 * (size_t)c->nranks, cudaMemcpyDeviceToHost);
+        cudaFree(dbuf);
+        for (int p = 0; p < c->nranks; ++p) {
+            if (p == c->rank) continue;
+            cudaError_t e = cudaIpcOpenMemHandle(&sh.peer[p], all[(size_t)p], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess)
+                return dfail(BSM_ERR_CUDA, std::string("cudaIpcOpenMemHandle (peer access between the GPUs of this box is required): ") +
+                                               cudaGetErrorString(e));
+        }
+    }
+    *out = sh;
+    return 0;
+}
+
+int ensure_flags(bsm_comm c) {
+    if (c->flags) return 0;
+    bsm_comm_s::Shared sh;
+    if (int rc = shared_alloc(c, sizeof(int32_t) * 2 * (size_t)c->nranks, &sh)) return rc;
+    c->flags = (int32_t *)sh.local;
+    if (cudaMalloc(&c->peer_flags_dev, sizeof(int32_t *) * 8) != cudaSuccess) return dfail(BSM_ERR_ALLOC, "cudaMalloc failed");
+    cudaMemcpy(c->peer_flags_dev, sh.peer, sizeof(void *) * 8, cudaMemcpyHostToDevice);
+    c->shared.push_back(sh);
+    return 0;
+}
+
+}  // namespace
+
+int bsm_dist_alloc(bsm_comm c, size_t bytes, void **dev_ptr) {
+    if (!c || !dev_ptr) return dfail(BSM_ERR_ARG, "null argument");
+    if (int rc = api_ok()) return rc;
+    bsm_comm_s::Shared sh;
+    if (int rc = shared_alloc(c, bytes, &sh)) return rc;
+    c->shared.push_back(sh);
+    *dev_ptr = sh.local;
+    return 0;
+}
+
+int bsm_dist_free(bsm_comm c, void *dev_ptr) {
+    if (!c) return dfail(BSM_ERR_ARG, "null communicator");
+    for (size_t i = 0; i < c->shared.size(); ++i) {
+        if (c->shared[i].local != dev_ptr) continue;
+        cudaDeviceSynchronize();
+        for (int p = 0; p < c->nranks; ++p)
+            if (p != c->rank && c->shared[i].peer[p]) cudaIpcCloseMemHandle(c->shared[i].peer[p]);
+        cudaFree(c->shared[i].local);
+        c->shared.erase(c->shared.begin() + (long)i);
+        return 0;
+    }
+    return dfail(BSM_ERR_ARG, "not an array of bsm_dist_alloc");
+}
+
+int bsm_mul_dist_peer(bsm_comm c, bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
+                      void *x_shared, void *y_dev, const int64_t *in_cuts, void *stream) {
+    if (!c || !h || !x_shared || !y_dev || !in_cuts) return dfail(BSM_ERR_ARG, "null argument");
+    if (c->nranks == 1) return bsm_mul(h, op, alpha, beta, beta_is_false, x_shared, 0, y_dev, 0, 1, stream);
+    if (int rc = ensure_flags(c)) return rc;   // may grow c->shared: look x up afterwards
+    const bsm_comm_s::Shared *sh = nullptr;
+    for (const auto &s : c->shared)
+        if (s.local == x_shared) sh = &s;
+    if (!sh) return dfail(BSM_ERR_ARG, "x must be an array of bsm_dist_alloc");
+    bsm::PeerX px;
+    px.npeer = c->nranks;
+    for (int p = 0; p < c->nranks; ++p) {
+        px.peer[p] = sh->peer[p];
+        px.cuts[p] = (int32_t)in_cuts[p];
+    }
+    px.cuts[c->nranks] = (int32_t)in_cuts[c->nranks];
+    cudaStream_t st = (cudaStream_t)stream;
+    const int32_t e = ++c->epoch;
+    // barrier 1: every rank's x slab of this epoch is written; then the multiply reads x where it lives;
+    // barrier 2: every rank has finished reading, so whatever follows on the stream may overwrite the slab
+    flag_signal_kernel<<<1, 32, 0, st>>>(c->peer_flags_dev, 0, c->rank, c->nranks, e);
+    flag_wait_kernel<<<1, 32, 0, st>>>(c->flags, 0, c->nranks, e);
+    void *unused = nullptr;
+    if (int rc = bsm_mul_phase(h, op, alpha, beta, beta_is_false, x_shared, y_dev, stream, 0, &unused, &px)) return rc;
+    flag_signal_kernel<<<1, 32, 0, st>>>(c->peer_flags_dev, 1, c->rank, c->nranks, e);
+    flag_wait_kernel<<<1, 32, 0, st>>>(c->flags, 1, c->nranks, e);
+    if (cudaGetLastError() != cudaSuccess) return dfail(BSM_ERR_CUDA, "flag kernels failed to launch");
+    return 0;
+}
+
 int bsm_dist_allreduce_max_f64(bsm_comm c, double *dev_values, int64_t count, void *stream) {
     if (!c || !dev_values) return dfail(BSM_ERR_ARG, "null argument");
     if (int rc = api_ok()) return rc;
@@ -285,14 +435,14 @@ int bsm_mul_dist(bsm_comm c, bsm_handle h, int op, const void *alpha, const void
             return dfail(BSM_ERR_CUDA, "event record/wait failed");
         if (int rc = bsm_dist_allgather_rows(c, bsm_dtype_of(h), x_dev, ldx, 1, in_cuts, (void *)c->comm_stream)) return rc;
         if (cudaEventRecord(c->ev_gathered, c->comm_stream) != cudaSuccess) return dfail(BSM_ERR_CUDA, "event record failed");
-        if (int rc = bsm_mul_phase(h, op, alpha, beta, beta_is_false, x_dev, y_dev, stream, 1, &scratch)) return rc;
+        if (int rc = bsm_mul_phase(h, op, alpha, beta, beta_is_false, x_dev, y_dev, stream, 1, &scratch, nullptr)) return rc;
         if (cudaStreamWaitEvent(c->aux_stream, c->ev_gathered, 0) != cudaSuccess) return dfail(BSM_ERR_CUDA, "event wait failed");
-        if (int rc = bsm_mul_phase(h, op, alpha, beta, beta_is_false, x_dev, y_dev, (void *)c->aux_stream, 2, &scratch)) return rc;
+        if (int rc = bsm_mul_phase(h, op, alpha, beta, beta_is_false, x_dev, y_dev, (void *)c->aux_stream, 2, &scratch, nullptr)) return rc;
         if (cudaEventRecord(c->ev_remote, c->aux_stream) != cudaSuccess ||
             cudaStreamWaitEvent(st, c->ev_remote, 0) != cudaSuccess ||
             cudaStreamWaitEvent(st, c->ev_gathered, 0) != cudaSuccess)
             return dfail(BSM_ERR_CUDA, "event record/wait failed");
-        if (int rc = bsm_mul_phase(h, op, alpha, beta, beta_is_false, x_dev, y_dev, stream, 3, &scratch)) return rc;
+        if (int rc = bsm_mul_phase(h, op, alpha, beta, beta_is_false, x_dev, y_dev, stream, 3, &scratch, nullptr)) return rc;
         if (scratch && cudaFreeAsync(scratch, st) != cudaSuccess) return dfail(BSM_ERR_CUDA, "scratch free failed");
         return 0;
     }

@@ -93,6 +93,27 @@ __device__ __forceinline__ Pack<T, V> load_stream(const T *p) {
     return r;
 }
 
+// ---- where x lives ---------------------------------------------------------------------------------
+// Single GPU: one array. Slab handles in peer mode (bsm_mul_dist_peer): every rank keeps a full-length x in
+// peer-mapped memory but only its own slab [cuts[r], cuts[r+1]) is current; element i is read straight from
+// its owner's array over NVLink (npeer > 0), so the all-gather disappears into the kernels' own x fetches.
+constexpr int kMaxPeers = 8;
+template <class T>
+struct XSrc {
+    const T *x;
+    const T *peer[kMaxPeers];
+    int32_t cuts[kMaxPeers + 1];
+    int32_t npeer;   // 0: plain array
+    __device__ __forceinline__ const T *ptr(int32_t i) const {
+        if (npeer == 0) return x + i;
+        int r = 0;
+#pragma unroll
+        for (int k = 1; k < kMaxPeers; ++k) r += (k < npeer && i >= cuts[k]) ? 1 : 0;
+        return peer[r] + i;
+    }
+    __device__ __forceinline__ T at(int32_t i) const { return *ptr(i); }
+};
+
 // ---- kernel arguments ------------------------------------------------------------------------
 template <class T>
 struct MulArgs {
@@ -104,7 +125,7 @@ struct MulArgs {
     const int32_t *set_start;
     const int64_t *set_pool_off;
     const int32_t *pool;
-    const T *x;
+    XSrc<T> x;
     T *y;
     T *scratch;
     T alpha, beta;
@@ -206,7 +227,7 @@ __device__ __forceinline__ void slice_body(const MulArgs<T> &a, const bsm_slice 
             for (int32_t j0 = 0; j0 < cb.n; j0 += kXsCap) {
                 const int32_t cn = min(kXsCap, cb.n - j0);
                 __syncthreads();
-                for (int32_t k = t; k < cn; k += kThreads) xs[k] = a.x[in.at(j0 + k)];
+                for (int32_t k = t; k < cn; k += kThreads) xs[k] = a.x.at(in.at(j0 + k));
                 __syncthreads();
                 if (rows_ok)
                     nform_chunk<T, V, CONJ>(blk + (int64_t)j0 * cb.m + r0 + iv * V, cb.m, cn, c, P, xs, acc);
@@ -217,7 +238,7 @@ __device__ __forceinline__ void slice_body(const MulArgs<T> &a, const bsm_slice 
             for (int32_t i0 = 0; i0 < cb.m; i0 += kXsCap) {
                 const int32_t cm = min(kXsCap, cb.m - i0);
                 __syncthreads();
-                for (int32_t k = t; k < cm; k += kThreads) xs[k] = a.x[in.at(i0 + k)];
+                for (int32_t k = t; k < cm; k += kThreads) xs[k] = a.x.at(in.at(i0 + k));
                 __syncthreads();
                 for (int32_t jj = warp; jj < hc; jj += kWarps) {
                     const T s = tform_column<T, V, CONJ>(blk + (int64_t)(r0 + jj) * cb.m + i0, cm, lane, xs);
@@ -290,7 +311,7 @@ __device__ __forceinline__ void fused_slice(const MulArgs<T> &a, const bsm_slice
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int32_t L = sl.r1;  // r0 == 0: the whole segment
     const SetRef out = set_ref(a, sl.out_set);
-    xrs[t] = (t < L) ? a.x[out.at(t)] : El<T>::zero();   // x at the segment's own rows
+    xrs[t] = (t < L) ? a.x.at(out.at(t)) : El<T>::zero();   // x at the segment's own rows
     accT[t] = El<T>::zero();
     T accN[RPL];
 #pragma unroll
@@ -307,7 +328,7 @@ __device__ __forceinline__ void fused_slice(const MulArgs<T> &a, const bsm_slice
             for (int32_t j0 = 0; j0 < cb.n; j0 += kXsCap) {
                 const int32_t cn = min(kXsCap, cb.n - j0);
                 __syncthreads();
-                for (int32_t k = t; k < cn; k += kFThreads) xs[k] = a.x[in.at(j0 + k)];
+                for (int32_t k = t; k < cn; k += kFThreads) xs[k] = a.x.at(in.at(j0 + k));
                 __syncthreads();
                 for (int32_t j = 2 * warp; j < cn; j += 2 * kFWarps) {
                     const bool hasB = (j + 1) < cn;
@@ -353,7 +374,7 @@ __device__ __forceinline__ void fused_slice(const MulArgs<T> &a, const bsm_slice
             for (int32_t i0 = 0; i0 < cb.m; i0 += kXsCap) {
                 const int32_t cm = min(kXsCap, cb.m - i0);
                 __syncthreads();
-                for (int32_t k = t; k < cm; k += kFThreads) xs[k] = a.x[in.at(i0 + k)];
+                for (int32_t k = t; k < cm; k += kFThreads) xs[k] = a.x.at(in.at(i0 + k));
                 __syncthreads();
                 for (int32_t jj = warp; jj < hc; jj += kFWarps) {
                     const T s = tform_column<T, 1, CONJ>(blk + (int64_t)jj * cb.m + i0, cm, lane, xs);
@@ -582,7 +603,7 @@ __device__ __forceinline__ void tma_consumer(const MulArgs<T> &a, const bsm_slic
     const SetRef out = set_ref(a, sl.out_set);
     // xrs is zero-padded to 256 rows and xs to the row count read below, so lanes past the block's
     // height multiply by zero
-    xrs[t] = (r0 == 0 && t < L) ? a.x[out.at(t)] : El<T>::zero();
+    xrs[t] = (r0 == 0 && t < L) ? a.x.at(out.at(t)) : El<T>::zero();
     accT[t] = El<T>::zero();
     T accN[RPL];
 #pragma unroll
@@ -605,14 +626,14 @@ __device__ __forceinline__ void tma_consumer(const MulArgs<T> &a, const bsm_slic
             // x at the block's rows, once per contribution (m <= kXsCap)
             const int32_t mpad = GEN ? max(m, kFMaxRows) : kFMaxRows;
             consumer_bar();
-            for (int32_t k = t; k < mpad; k += kFThreads) xs[k] = (k < m) ? a.x[in.at(k)] : El<T>::zero();
+            for (int32_t k = t; k < mpad; k += kFThreads) xs[k] = (k < m) ? a.x.at(in.at(k)) : El<T>::zero();
             consumer_bar();
         }
         for (int32_t jw = jlo; jw < jhi; jw += kXsCap) {
             const int32_t wend = min(jhi, jw + kXsCap);
             if (!tform) {
                 consumer_bar();
-                for (int32_t k = t; k < wend - jw; k += kFThreads) xs[k] = a.x[in.at(jw + k)];
+                for (int32_t k = t; k < wend - jw; k += kFThreads) xs[k] = a.x.at(in.at(jw + k));
                 consumer_bar();
             }
             for (int32_t j0 = jw; j0 < wend; j0 += cc, ++q) {
@@ -763,7 +784,7 @@ struct WarpArgs {
     const bsm_wchunk *chunks;
     const int32_t *item_ptr;
     const int32_t *pool;
-    const T *x;
+    XSrc<T> x;
     T *y;
     T *scratch;
     T alpha, beta;
@@ -985,10 +1006,10 @@ __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned 
             const uint32_t fl = d.flags();
             if (!(fl & 2u)) {
                 const int32_t cnt = (fl & 1u) ? d.m() : d.ncols();
-                const T *src = a.x + d.x_ref();
+                const int32_t xr = d.x_ref();
                 T *xd = reinterpret_cast<T *>(dst + bytes);
-                if (lane < cnt) cp_async_elem<(int)sizeof(T)>(xd + lane, src + lane);
-                if (lane + 32 < cnt) cp_async_elem<(int)sizeof(T)>(xd + lane + 32, src + lane + 32);
+                if (lane < cnt) cp_async_elem<(int)sizeof(T)>(xd + lane, a.x.ptr(xr + lane));
+                if (lane + 32 < cnt) cp_async_elem<(int)sizeof(T)>(xd + lane + 32, a.x.ptr(xr + lane + 32));
             }
             cp_async_mbar_arrive_noinc(bar);
             ++ii;
@@ -1023,8 +1044,8 @@ __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned 
         if (fl & 2u) {
             // arbitrary index vector: gather x through the pool into the warp's staging array
             const int32_t cnt = tform ? m : nc;
-            xs[lane] = (lane < cnt) ? a.x[__ldg(a.pool + d0.x_ref() + lane)] : El<T>::zero();
-            xs[lane + 32] = (lane + 32 < cnt) ? a.x[__ldg(a.pool + d0.x_ref() + lane + 32)] : El<T>::zero();
+            xs[lane] = (lane < cnt) ? a.x.at(__ldg(a.pool + d0.x_ref() + lane)) : El<T>::zero();
+            xs[lane + 32] = (lane + 32 < cnt) ? a.x.at(__ldg(a.pool + d0.x_ref() + lane + 32)) : El<T>::zero();
             xin = xs;
         }
         __syncwarp();

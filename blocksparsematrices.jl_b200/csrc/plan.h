@@ -167,6 +167,13 @@ void layout_arena(HostMatrix &M);
 std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t out_dim,
                        int64_t in_dim, const PlanParams &pp, HostPlan &P);
 
+// ---- dist.cu -> abi.cu: x read straight from its owners' peer-mapped arrays (bsm_mul_dist_peer) -----------
+struct PeerX {
+    const void *peer[8];
+    int32_t cuts[9];
+    int32_t npeer = 0;
+};
+
 // ---- sparse.cu <-> abi.cu (the handle's internals stay in abi.cu) --------------------------------------
 struct SparseSource {
     const HostMatrix *H;

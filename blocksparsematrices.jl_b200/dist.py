@@ -64,6 +64,27 @@ class Comm:
         L.check(L.lib().bsm_dist_allgather_rows(self._h, dt, c_void_p(x.data_ptr()), ldx, nrhs,
                                                 c.ctypes.data_as(POINTER(c_int64)), c_void_p(st)))
 
+    def alloc(self, n: int, dtype):
+        """Collective: a length-n CUDA tensor of `dtype` in memory that every rank of the box maps (bsm_dist_alloc,
+        CUDA IPC). Keep x in such a tensor to use SlabMatrix.mul_peer; release it with free()."""
+        import torch
+        dt = np.dtype(dtype)
+        p = c_void_p()
+        L.check(L.lib().bsm_dist_alloc(self._h, n * dt.itemsize, byref(p)))
+
+        class _Holder:   # __cuda_array_interface__ view of the raw allocation (owned by the communicator)
+            pass
+
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": (n,), "typestr": dt.str, "data": (p.value, False), "version": 3,
+                                      "strides": None}
+        t = torch.as_tensor(h, device=torch.device("cuda", self.device))
+        t._bsm_holder = h
+        return t
+
+    def free(self, t):
+        L.check(L.lib().bsm_dist_free(self._h, c_void_p(t.data_ptr())))
+
     def allreduce_max(self, t, stream=None):
         import torch
         assert t.dtype == torch.float64 and t.is_cuda
@@ -123,4 +144,22 @@ class SlabMatrix:
                                      b.ctypes.data_as(c_void_p), int(beta_false), c_void_p(x.data_ptr()), ldx,
                                      c_void_p(y.data_ptr()), ldy, nrhs,
                                      self.cuts.ctypes.data_as(POINTER(c_int64)), c_void_p(st)))
+        return y
+
+    def mul_peer(self, op, x_shared, y, alpha=True, beta=False, stream=None):
+        """y[own] = alpha*op(A_slab)*x + beta*y[own] with NO collective: x_shared is a tensor of Comm.alloc of which
+        this rank has written its own slab; the kernels read every other entry from its owner over NVLink
+        (bsm_mul_dist_peer: flag barrier, multiply, flag barrier)."""
+        import torch
+        D = self.local
+        beta_false = isinstance(beta, (bool, np.bool_)) and not beta
+        a = np.array([alpha], dtype=D.dtype)
+        b = np.array([0 if beta_false else beta], dtype=D.dtype)
+        if x_shared.dim() != 1 or x_shared.dtype != _torch_dtype(D.dtype) or y.dtype != x_shared.dtype:
+            raise TypeError("x and y must be 1-D CUDA tensors of the operator's dtype")
+        st = torch.cuda.current_stream(x_shared.device).cuda_stream if stream is None else stream
+        L.check(L.lib().bsm_mul_dist_peer(self.comm._h, D._h, _OPS[op], a.ctypes.data_as(c_void_p),
+                                          b.ctypes.data_as(c_void_p), int(beta_false), c_void_p(x_shared.data_ptr()),
+                                          c_void_p(y.data_ptr()), self.cuts.ctypes.data_as(POINTER(c_int64)),
+                                          c_void_p(st)))
         return y

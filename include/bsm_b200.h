@@ -282,6 +282,17 @@ int bsm_dist_info(bsm_comm c, int *nranks, int *rank, int *nccl_version);
 int bsm_dist_allgather_rows(bsm_comm c, int dtype, void *x_dev, int64_t ldx, int64_t nrhs, const int64_t *cuts,
                             void *stream);
 int bsm_dist_allreduce_max_f64(bsm_comm c, double *dev_values, int64_t count, void *stream);
+/* Peer mode — the all-gather fused into the multiply. bsm_dist_alloc is collective: every rank allocates `bytes`
+ * on its GPU and maps every peer's allocation (CUDA IPC, NVLink peer access). Keep a full-length x in such an
+ * array; a rank only ever writes its own slab. bsm_mul_dist_peer (nrhs = 1) runs NO collective: after a flag
+ * barrier ("every slab of this epoch is written") the multiply kernels fetch each x element from its owner's
+ * array over NVLink with the same asynchronous copies that stage it from local HBM (only the entries the rank's
+ * blocks touch ever cross the link), and a second flag barrier ("every rank has finished reading") orders
+ * whatever follows on the stream — e.g. the solver's update of the slab — after the peers' reads. */
+int bsm_dist_alloc(bsm_comm c, size_t bytes, void **dev_ptr);
+int bsm_dist_free(bsm_comm c, void *dev_ptr);
+int bsm_mul_dist_peer(bsm_comm c, bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
+                      void *x_shared, void *y_dev, const int64_t *in_cuts, void *stream);
 /* all-gather of x over in_cuts, then bsm_mul on this rank's slab. */
 int bsm_mul_dist(bsm_comm c, bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
                  void *x_dev, int64_t ldx, void *y_dev, int64_t ldy, int64_t nrhs, const int64_t *in_cuts,

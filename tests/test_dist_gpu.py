@@ -74,6 +74,19 @@ def _worker(rank, world, port, q):
             else:
                 ref = np.stack([oracle_mul(A, np.ascontiguousarray(xt[:, j]), op) for j in range(nrhs)], axis=1)[lo:hi]
             errs[(name, op)] = rel2(got, ref)
+            if nrhs == 1:
+                # peer mode: no collective at all, x read from its owners over NVLink; two epochs in a row
+                xs = comm.alloc(n, A.dtype)
+                for epoch in range(2):
+                    xs.fill_(float("nan"))
+                    xs[lo:hi] = torch.from_numpy((1 + epoch) * xt[lo:hi]).cuda()
+                    y3 = torch.zeros_like(xs)
+                    SM.mul_peer(op, xs, y3)
+                    torch.cuda.synchronize()
+                    assert rel2(y3.cpu().numpy()[lo:hi], (1 + epoch) * ref) < 1e-12, ("peer", name, op, epoch)
+                    assert torch.isnan(xs[:lo]).all() and torch.isnan(xs[hi:]).all()      # nothing was gathered
+                dist.barrier()
+                comm.free(xs)
             assert not np.any(y.cpu().numpy()[:lo] != 0) and not np.any(y.cpu().numpy()[hi:] != 0)
     out = [None] * world
     dist.all_gather_object(out, errs)
