@@ -106,7 +106,12 @@ struct bsm_matrix {
     bool restricted = false;
     // benchmarking: events around the kernels of the last bsm_mul
     bool profiling = false;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    // a ring of event triples: every bsm_mul while profiling is on records into the next slot, so a whole timed
+    // region of back-to-back multiplies can be read afterwards (bsm_get_profile averages and resets)
+    static constexpr int kProfSlots = 64;
+    std::vector<cudaEvent_t> ev_ring;
+    cudaEvent_t *ev = nullptr;      // the slot of the multiply being launched
+    int64_t prof_count = 0;
 };
 
 namespace {
@@ -391,6 +396,10 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
     const HostPlan &HP = A->H.plan[p];
     const DevPlan &DP = A->plan[p];
     T *scratch = nullptr;
+    if (A->profiling && phase <= 1) {   // next slot of the event ring (one per multiply)
+        A->ev = A->ev_ring.data() + 3 * (A->prof_count % bsm_matrix::kProfSlots);
+        A->prof_count++;
+    }
     if (phase != 0 && (nrhs != 1 || p >= 4 || !scratch_io)) return fail(BSM_ERR_ARG, "phased multiply needs nrhs = 1");
     if (px && px->npeer > 0 && (nrhs != 1 || p >= 4)) return fail(BSM_ERR_ARG, "peer-mode multiply needs nrhs = 1");
     const int32_t nfused = (int32_t)HP.n_fused_slices;
@@ -900,8 +909,7 @@ int bsm_destroy(bsm_handle h) {
     if (h->hx) cudaFree(h->hx);
     if (h->hy) cudaFree(h->hy);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
-    for (int i = 0; i < 3; ++i)
-        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (cudaEvent_t e : h->ev_ring) cudaEventDestroy(e);
     delete h;
     return 0;
 }
@@ -920,22 +928,35 @@ int bsm_set_profiling(bsm_handle h, int on) {
     if (int rc = check_handle(h)) return rc;
     if (h->device == BSM_DEVICE_NONE) return fail(BSM_ERR_CUDA, "host-only handle");
     DeviceGuard g(h->device);
-    if (on && !h->ev[0])
-        for (int i = 0; i < 3; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
+    if (on && h->ev_ring.empty()) {
+        h->ev_ring.resize(3 * bsm_matrix::kProfSlots);
+        for (auto &e : h->ev_ring) CUDA_TRY(cudaEventCreate(&e));
+    }
     h->profiling = on != 0;
+    h->prof_count = 0;
+    h->ev = h->ev_ring.empty() ? nullptr : h->ev_ring.data();
     return 0;
 }
 
 int bsm_get_profile(bsm_handle h, double *main_ms, double *finalize_ms) {
     if (int rc = check_handle(h)) return rc;
-    if (!h->profiling || !h->ev[0]) return fail(BSM_ERR_ARG, "profiling is off");
+    if (!h->profiling || h->ev_ring.empty()) return fail(BSM_ERR_ARG, "profiling is off");
+    if (h->prof_count == 0) return fail(BSM_ERR_ARG, "no multiply has been recorded since profiling was switched on");
     DeviceGuard g(h->device);
-    CUDA_TRY(cudaEventSynchronize(h->ev[2]));
-    float a = 0.f, b = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
-    CUDA_TRY(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
-    if (main_ms) *main_ms = a;
-    if (finalize_ms) *finalize_ms = b;
+    const int64_t n = std::min<int64_t>(h->prof_count, bsm_matrix::kProfSlots);
+    double sa = 0.0, sb = 0.0;
+    for (int64_t k = 0; k < n; ++k) {
+        cudaEvent_t *e = h->ev_ring.data() + 3 * ((h->prof_count - 1 - k) % bsm_matrix::kProfSlots);
+        CUDA_TRY(cudaEventSynchronize(e[2]));
+        float a = 0.f, b = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&a, e[0], e[1]));
+        CUDA_TRY(cudaEventElapsedTime(&b, e[1], e[2]));
+        sa += a;
+        sb += b;
+    }
+    if (main_ms) *main_ms = sa / (double)n;
+    if (finalize_ms) *finalize_ms = sb / (double)n;
+    h->prof_count = 0;
     return 0;
 }
 

@@ -138,10 +138,12 @@ int bsm_mul_host(bsm_handle h, int op, const void *alpha, const void *beta, int 
 
 int bsm_set_variant(bsm_handle h, int variant);
 
-/* Per-kernel device timing for roofline reports: when on, bsm_mul brackets each of its kernels with
- * CUDA events on the launch stream (nrhs = 1 only). bsm_get_profile synchronises on the last
- * recorded events and returns the milliseconds of the main multiply kernel and of the gather
- * (finalize) kernel of the most recent bsm_mul. Not thread-safe; benchmarking only. */
+/* Per-kernel device timing for roofline reports: when on, bsm_mul brackets its multiply kernels and its gather
+ * (finalize) kernel with CUDA events on the launch stream, one event triple per call in a ring of 64.
+ * bsm_get_profile synchronises on the recorded events and returns the AVERAGE milliseconds of the main multiply
+ * kernel(s) and of the gather kernel over the calls made since profiling was switched on / last read (at most
+ * the last 64), then resets — so a timed region of back-to-back multiplies can be read afterwards. Not
+ * thread-safe; benchmarking only. */
 int bsm_set_profiling(bsm_handle h, int on);
 int bsm_get_profile(bsm_handle h, double *main_ms, double *finalize_ms);
 
