@@ -538,7 +538,8 @@ def main():
                      "finalize_ms": float(np.mean(fin_ms)), "peak_source": peak_src,
                      "bytes_per_launch": local_work["bytes"]},
         "e2e": e2e,
-        "gpu_launches": int(args.steps * (D.launch_count(op) if nrhs == 1 or tensor is None else 1)),
+        # our kernels per step: the multiply's own launches (+ the four flag-barrier kernels of peer mode)
+        "gpu_launches": int(args.steps * ((D.launch_count(op) if nrhs == 1 or tensor is None else 1) + (4 if peer else 0))),
         "clocks": clocks,
     }
     if tensor is not None:

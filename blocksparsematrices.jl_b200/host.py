@@ -74,6 +74,9 @@ class AbstractBlockMatrix:
 
     __matmul__ = __mul__
 
+    def __getitem__(self, key):
+        return _getindex(self, key)
+
     # -- device mirror (the package-extension constructor; built on first use)
     def device(self, **kw):
         from .device import DeviceMatrix
@@ -106,6 +109,9 @@ class _Wrapped:
         return _apply(self.lmap, self._op, x)
 
     __matmul__ = __mul__
+
+    def __getitem__(self, key):
+        return _getindex(self, key)
 
 
 class AdjointMap(_Wrapped):
@@ -143,6 +149,23 @@ def _unwrap(A):
 def _apply(A, op, x):
     from .device import apply
     return apply(A, op, x)
+
+
+def _getindex(A, key):
+    """A[i, j], A[:, j], A[i, :], A[:, :] as LinearMaps does it (getindex through products with unit vectors,
+    the way the reference's tests materialise `b[:, :]`, test/test_blockmatrix.jl:38-49): the selected columns
+    are ONE multi-RHS product on the GPU. Indices are 0-based here (Python), slices and integer arrays allowed."""
+    if not isinstance(key, tuple) or len(key) != 2:
+        raise IndexError("block matrices are indexed with two subscripts")
+    nr, nc = A.size
+    rows = np.arange(nr)[key[0]]
+    cols = np.arange(nc)[key[1]]
+    cvec = np.atleast_1d(cols)
+    X = np.zeros((nc, len(cvec)), dtype=A.dtype, order="F")
+    X[cvec, np.arange(len(cvec))] = 1
+    Y = A * X if len(cvec) else np.zeros((nr, 0), A.dtype)
+    out = Y[rows] if np.ndim(cols) else Y[rows, 0]
+    return out
 
 
 def mul_(y, A, x, alpha=True, beta=False):

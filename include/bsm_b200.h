@@ -292,7 +292,7 @@ int bsm_dist_allreduce_max_f64(bsm_comm c, double *dev_values, int64_t count, vo
  * blocks touch ever cross the link), and a second flag barrier ("every rank has finished reading") orders
  * whatever follows on the stream — e.g. the solver's update of the slab — after the peers' reads. */
 int bsm_dist_alloc(bsm_comm c, size_t bytes, void **dev_ptr);
-int bsm_dist_free(bsm_comm c, void *dev_ptr);
+int bsm_dist_free(bsm_comm c, void *dev_ptr);   /* only after every rank has finished its last multiply on it */
 int bsm_mul_dist_peer(bsm_comm c, bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
                       void *x_shared, void *y_dev, const int64_t *in_cuts, void *stream);
 /* all-gather of x over in_cuts, then bsm_mul on this rank's slab. */

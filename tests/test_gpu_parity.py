@@ -109,6 +109,14 @@ def test_materialised_matrix(golden):
     assert np.max(np.abs(A * X - S[:, cols])) < 1e-13
     assert np.max(np.abs(B.adjoint(A) * X - S.conj().T[:, cols])) < 1e-13
     assert np.max(np.abs(B.transpose(A) * X - S.T[:, cols])) < 1e-13
+    # getindex the LinearMaps way: b[:, :], adjoint(b)[:, :], single entries and slices
+    m = min(n, 300)
+    assert np.max(np.abs(A[:, :m] - S[:, :m])) < 1e-13
+    assert np.max(np.abs(B.adjoint(A)[:, :m] - S.conj().T[:, :m])) < 1e-13
+    assert abs(A[5, 7] - S[5, 7]) < 1e-13 and np.max(np.abs(A[3:9, 11] - S[3:9, 11])) < 1e-13
+    E = O.sbm_to_bsm(golden)
+    Ab = B.BlockSparseMatrix(E.blocks, E.rowindices, E.colindices, E.size)
+    assert np.max(np.abs(B.transpose(Ab)[:, :m] - B.sparse(Ab).toarray().T[:, :m])) < 1e-13
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
