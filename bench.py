@@ -367,6 +367,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    barrier()          # ranks finish generating / packing at different times
     for _ in range(args.warmup):
         step()
     barrier()

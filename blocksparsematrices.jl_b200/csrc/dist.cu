@@ -301,7 +301,7 @@ __global__ void flag_wait_kernel(const int32_t *flags, int which, int nranks, in
     const long long t0 = clock64();
     while (*f < epoch) {
         __nanosleep(100);
-        if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s: a peer died or never entered the collective call
+        if (clock64() - t0 > 120000000000ll) __trap();   // ~60 s: a peer died or never entered the collective call
     }
     __threadfence_system();
 }
