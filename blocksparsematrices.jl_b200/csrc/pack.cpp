@@ -1,6 +1,7 @@
-// pack.cpp — host packer: index-set deduplication, arena layout, plan construction.
-// Everything here is deterministic (no hashing order leaks into the tables) so the Python mirror
-// (blocksparsematrices.jl_b200/packing.py) reproduces every table bit for bit.
+// pack.cpp — host packer: index-set deduplication, arena layout, plan construction (slicing, ownership, static
+// shared-memory schedules of the warp-stream kernel, local/remote phases of slab handles, colour-ordered plans).
+// Everything here is deterministic (no hashing order leaks into the tables): the same input gives bit-identical
+// tables with or without a device, which is what the CPU tests replay with the NumPy plan interpreter.
 #include "plan.h"
 
 #include <algorithm>

@@ -131,8 +131,8 @@ int bsm_destroy(bsm_handle h);
 int bsm_mul(bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
             const void *x_dev, int64_t ldx, void *y_dev, int64_t ldy, int64_t nrhs, void *stream);
 
-/* Same with HOST x / y: H2D of x (and of y when beta is used), multiply, D2H of y, then
- * synchronises. Uses pinned staging buffers owned by the handle (serialised per handle). */
+/* Same with HOST x / y (pageable or pinned): H2D of x (and of y when beta is used) into device buffers owned by
+ * the handle, multiply, D2H of y, then synchronises (serialised per handle). */
 int bsm_mul_host(bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
                  const void *x_host, int64_t ldx, void *y_host, int64_t ldy, int64_t nrhs);
 
