@@ -73,6 +73,18 @@ def test_symmetric_fixture(golden):
     assert abs(S - S.T).nnz == 0                                 # issymmetric, :49
 
 
+@pytest.mark.parametrize("name", ["cuboid", "sphere"])
+def test_frozen_products_on_the_fixture(name):
+    """Known answers (tests/golden/products_*.npz) on the reference's shipped fixture through the C ABI."""
+    from pathlib import Path
+    g = O.load_golden_sbm(name)
+    z = np.load(Path(__file__).resolve().parent / "golden" / f"products_{name}.npz")
+    A = B.SymmetricBlockMatrix(g.diagonals, g.diagonalindices, g.offdiagonals, g.rowindices, g.colindices, g.size)
+    for op in OPS:
+        assert rel2(wrap(A, op) * z["x"], z[f"y_{op}"]) < 1e-12
+        assert rel2(B.mul_(z["y0"].copy(), wrap(A, op), z["x"], 1j, 2j), z[f"y5_{op}"]) < 1e-12
+
+
 def test_blocksparse_fixture(golden):
     E = O.sbm_to_bsm(golden)
     A = B.BlockSparseMatrix(E.blocks, E.rowindices, E.colindices, E.size)

@@ -200,3 +200,43 @@ def test_real_dtypes(dt):
     xt = rng.standard_normal(15).astype(dt)
     reft = O.sparse_bsm(B).astype(np.float64).T @ xt.astype(np.float64)
     assert relmax(O.c_mul_bsm(B, xt, "T").astype(np.float64), reft) < tol
+
+
+@pytest.mark.parametrize("op", ["N", "T", "C"])
+def test_frozen_products(sbm, op):
+    """Known answers on the shipped fixture (tests/golden/products_*.npz, made by make_products.py from the CSC
+    product): the C oracle, the NumPy oracle and the expanded BlockSparseMatrix / VBCRS forms all reproduce them."""
+    from pathlib import Path
+    name, A = sbm
+    z = np.load(Path(__file__).resolve().parent / "golden" / f"products_{name}.npz")
+    x, y0 = z["x"], z["y0"]
+    assert relmax(O.mul_sbm(A, x, op), z[f"y_{op}"]) < 1e-13
+    assert relmax(O.c_mul_sbm(A, x, op, threads=4), z[f"y_{op}"]) < 1e-13
+    assert relmax(O.c_mul_sbm(A, x, op, 1j, 2j, False, y0.copy(), 4), z[f"y5_{op}"]) < 1e-13
+    E = O.sbm_to_bsm(A)
+    assert relmax(O.c_mul_bsm(E, x, op, threads=4), z[f"y_{op}"]) < 1e-13
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_oracles_agree_on_random_structures(seed):
+    """C oracle = NumPy oracle = SciPy CSC product on random overlapping structures (all three storage types)."""
+    rng = np.random.default_rng(400 + seed)
+    nr, nc = int(rng.integers(60, 200)), int(rng.integers(60, 200))
+    blocks, rows, cols = [], [], []
+    for _ in range(int(rng.integers(10, 40))):
+        m, n = int(rng.integers(1, 30)), int(rng.integers(1, 30))
+        r0, c0 = int(rng.integers(1, nr - min(m, nr) + 2)), int(rng.integers(1, nc - min(n, nc) + 2))
+        m, n = min(m, nr - r0 + 1), min(n, nc - c0 + 1)
+        blocks.append(np.asfortranarray(rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))))
+        rows.append(np.arange(r0, r0 + m))
+        cols.append(np.arange(c0, c0 + n))
+    A = O.OBSM(blocks, rows, cols, (nr, nc))
+    S = O.sparse_bsm(A)
+    V = O.vbcrs_from_blocks(blocks, [r[0] for r in rows], [c[0] for c in cols], (nr, nc))
+    for op, M in (("N", S), ("T", S.T), ("C", S.conj().T)):
+        x = rng.standard_normal(M.shape[1]) + 1j * rng.standard_normal(M.shape[1])
+        ref = M @ x
+        assert relmax(O.mul_bsm(A, x, op), ref) < 1e-12
+        assert relmax(O.c_mul_bsm(A, x, op, threads=4), ref) < 1e-12
+        assert relmax(O.mul_vbcrs(V, x, op), ref) < 1e-12
+        assert relmax(O.c_mul_vbcrs(V, x, op, threads=4), ref) < 1e-12      # overlapping block rows: serial schedule
