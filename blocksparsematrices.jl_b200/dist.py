@@ -116,9 +116,11 @@ class SlabMatrix:
     def __init__(self, A, comm: Comm, cuts=None, ops=("N",), variant=L.VARIANT_AUTO):
         self.comm = comm
         self.size = A.size
+        if A.size[0] != A.size[1]:
+            # one set of cuts is both the partition of y (this rank's output slab) and of x (the slab it owns
+            # before the exchange): that is the solver-loop convention and needs a square operator
+            raise NotImplementedError("slab partition of a non-square operator (separate row / column cuts)")
         if cuts is None:
-            if A.size[0] != A.size[1] and len(ops) > 1:
-                raise ValueError("one set of cuts serves rows and columns only for square matrices")
             cuts = slab_cuts(A, comm.nranks, "N" if "N" in ops else "T")
             lo, hi = int(cuts[comm.rank]), int(cuts[comm.rank + 1])
             A = extract_slab(A, lo, hi, ops)
