@@ -1,27 +1,36 @@
 #!/usr/bin/env python
-"""bench.py — block SpMV throughput of the B200 multiply path (BASELINE.json metric).
+"""bench.py — block SpMV / SpMM throughput of the B200 multiply path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3|c1|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c1..c5]
 
-A "step" is one multiply y = A*x (mul!(y, A, x)) over the whole synthetic matrix.
-N = 1 workload (default): configs[1] of BASELINE.json — SymmetricBlockMatrix ComplexF64, 1 M unknowns,
-leaves 20–200, half-stored off-diagonals (~12.7 GB in HBM); working set >> L2, so no L2 flush is needed.
-N > 1 (torchrun): the same matrix cut into N nnz-balanced block-row slabs, one per rank; every step
-all-gathers x over NCCL and each rank writes its own y slice ("scaling": "strong").
+A "step" is one multiply y = op(A)*x (mul!(y, A, x)) over the whole synthetic matrix.
+Default workload: configs[1] of BASELINE.json ("c2") — SymmetricBlockMatrix ComplexF64, 1 M unknowns, leaves
+20–200, half-stored off-diagonals (~12.8 GB in HBM; working set >> L2, no flush needed). With the default
+workload the line also carries `also`: compact results of c3 (VBCRS Float64, 4 M rows) and c5 (BlockSparseMatrix
+Float64 x 64 right-hand sides), the two other configurations BASELINE.json names for 1/2/4/8 GPUs.
 
-Prints ONE JSON line (rank 0). `value` = algorithmic GB/s with operands resident in HBM (CUDA events,
-max over ranks); `e2e` = the same metric through the C-ABI host-pointer call (bsm_mul_host) from pinned
-host buffers, H2D of x and D2H of y inside the timed region; `roofline` = the dominant kernel against the
-measured HBM peak; `cpu_baseline` = the oracle (C restatement of the reference schedule) on the host
-cores over a bounded sample.  --impl reference times that CPU restatement alone (Julia is not
-installable in this image, so the oracle port stands in for the reference's threaded mul!).
+N > 1 (torchrun, one process per GPU):
+  c2, c3   nnz-balanced block-row slabs, x kept sharded in peer-mapped arrays; the multiply kernels fetch the x
+           entries they need from their owners over NVLink and carry both barriers themselves (no collective, no
+           extra launch) — bsm_mul_dist_peer;
+  c5       the 64 right-hand sides are split across the ranks, A replicated (1.6 GB): no exchange at all.
+"scaling": "strong" (the total work is fixed as N grows).
+
+ONE JSON line (rank 0). `value` = algorithmic GB/s with operands resident in HBM (CUDA events, max over ranks);
+algorithmic bytes = stored entries * s + (inputs + outputs) * s * nrhs, half-stored blocks counted once, index
+tables NOT counted (SURVEY §8d "without" figure — identical for the reference arm). `parity` = rel ||dy||/||y|| of
+the GPU result against the C oracle on the SAME full-size matrix and x (every rank checks its own y slice; the run
+fails above the tolerance). `e2e` = the same metric through the host-pointer C-ABI call (bsm_mul_host /
+bsm_mul_dist_peer_host) from pinned host buffers, H2D of x and D2H of y inside the timed region. `roofline` = the
+dominant kernel against the measured HBM peak. `cpu_baseline` / --impl reference = the oracle (C restatement of the
+reference schedule; Julia cannot be installed in this image) on the host cores, same matrix, same x; the reference
+arm never loads libbsm_b200.so.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -34,355 +43,318 @@ sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 
 METRIC = "block SpMV effective HBM GB/s"
+ALSO = ("c3", "c5")
+TOL = {"f32": 1e-5, "f64": 1e-12, "c128": 1e-12}
+NPDT = {"c128": np.complex128, "f64": np.float64, "f32": np.float32}
 
 
 # ----------------------------------------------------------------------------- workloads
-def workload_spec(name, scale):
+def workload_spec(name, scale, hard=""):
     if name == "c2":
         n = max(2000, int(1_000_000 * scale))
-        return dict(kind="SymmetricBlockMatrix", dtype="c128", n=n,
-                    desc=f"C2 SymmetricBlockMatrix ComplexF64 N={n} leaves 20-200 k_near=6 half-stored, mul!(y,A,x)")
+        tag = {"": "", "permuted": " PERMUTED (arbitrary unsorted index vectors)",
+               "scattered": " SCATTERED near leaves (drawn from all lower leaves)",
+               "permuted+scattered": " PERMUTED + SCATTERED"}[hard]
+        return dict(kind="SymmetricBlockMatrix", dtype="c128", n=n, op="N",
+                    desc=f"C2 SymmetricBlockMatrix ComplexF64 N={n} leaves 20-200 k_near=6 half-stored{tag}, mul!(y,A,x)")
     if name == "c3":
         n = max(2000, int(4_000_000 * scale))
-        return dict(kind="VBCRS", dtype="f64", n=n,
-                    desc=f"C3 VBCRS Float64 {n} rows blocks 8-64, mul!(y,A,x)")
+        return dict(kind="VBCRS", dtype="f64", n=n, op="N", desc=f"C3 VBCRS Float64 {n} rows blocks 8-64, mul!(y,A,x)")
     if name == "c1":
-        return dict(kind="BlockSparseMatrix", dtype="f64", n=10_000,
+        return dict(kind="BlockSparseMatrix", dtype="f64", n=10_000, op="N",
                     desc="C1 BlockSparseMatrix Float64 10000^2, 2000 blocks 32x32, y=A*x (L2-resident)")
     if name == "c4":
         g = max(4, int(round(64 * np.sqrt(scale))))
-        return dict(kind="BlockSparseMatrix", dtype="f32", n=g * 1024, grid=g,
+        return dict(kind="BlockSparseMatrix", dtype="f32", n=g * 1024, grid=g, op="T",
                     desc=f"C4 BlockSparseMatrix Float32 1024^2 blocks 5% of {g}x{g} grid, transpose(A)*x")
     if name == "c5":
         n = max(6400, int(1_000_000 * scale) // 32 * 32)
-        return dict(kind="BlockSparseMatrix", dtype="f64", n=n, nblocks=max(1000, int(200_000 * scale)), nrhs=64,
-                    desc=f"C5 BlockSparseMatrix Float64 N={n}, {max(1000, int(200_000 * scale))} blocks 32x32, "
-                         f"Y = A*X with 64 right-hand sides (SpMM)")
+        nb = max(1000, int(200_000 * scale))
+        return dict(kind="BlockSparseMatrix", dtype="f64", n=n, nblocks=nb, nrhs=64, op="N",
+                    desc=f"C5 BlockSparseMatrix Float64 N={n}, {nb} blocks 32x32, Y = A*X with 64 right-hand sides (SpMM)")
     raise SystemExit(f"unknown workload {name}")
 
 
-def build_workload(name, scale, rank=0, world=1, threads=8):
-    """Returns (host matrix of this rank's slab, op, owned range (lo, hi) or None, x slice bounds per rank)."""
+def build_workload(name, scale, rank=0, world=1, threads=8, hard=""):
+    """Returns (host matrix — for c2 on N > 1 only this rank's slab —, slab row bounds per rank or None)."""
     from bsm_b200 import generators as G
-    spec = workload_spec(name, scale)
+    spec = workload_spec(name, scale, hard)
     if name == "c2":
+        kw = dict(permuted="permuted" in hard, scattered="scattered" in hard)
         if world == 1:
-            return G.symmetric_nearfield(seed=2, n=spec["n"], threads=threads), "N", None, None
-        S = G.NearfieldStructure(2, spec["n"], 20, 200, 6)
+            return G.symmetric_nearfield(seed=2, n=spec["n"], threads=threads, **kw), None
+        S = G.NearfieldStructure(2, spec["n"], 20, 200, 6, scattered=kw["scattered"])
         cuts = S.partition(world)
-        A = G.symmetric_nearfield(seed=2, n=spec["n"], threads=threads, leaves=(int(cuts[rank]), int(cuts[rank + 1])))
-        rb = S.bounds[cuts]
-        return A, "N", (int(rb[rank]), int(rb[rank + 1])), rb
+        A = G.symmetric_nearfield(seed=2, n=spec["n"], threads=threads, leaves=(int(cuts[rank]), int(cuts[rank + 1])), **kw)
+        return A, S.bounds[cuts]
     if name == "c3":
-        return G.vbcrs_variable(seed=3, n=spec["n"], threads=threads), "N", None, None
+        return G.vbcrs_variable(seed=3, n=spec["n"], threads=threads), None
     if name == "c1":
-        return G.blocksparse_uniform(seed=1, threads=threads), "N", None, None
+        return G.blocksparse_uniform(seed=1, threads=threads), None
     if name == "c5":
-        return G.blocksparse_uniform(seed=5, n=spec["n"], nblocks=spec["nblocks"], threads=threads), "N", None, None
-    return G.blocksparse_large(seed=4, grid=spec["grid"], threads=threads), "T", None, None
+        return G.blocksparse_uniform(seed=5, n=spec["n"], nblocks=spec["nblocks"], threads=threads), None
+    return G.blocksparse_large(seed=4, grid=spec["grid"], threads=threads), None
+
+
+def host_work(A, op, nrhs=1):
+    """Algorithmic bytes / flops of one multiply from the HOST container alone (no library call): stored entries
+    once (half-stored symmetric blocks counted once), x read once, y written once, no index tables."""
+    s = np.dtype(A.dtype).itemsize
+    if hasattr(A, "offdiagonals"):
+        d = sum(int(b.size) for b in A.diagonals)
+        o = sum(int(b.size) for b in A.offdiagonals)
+        stored, applied = d + o, d + 2 * o
+    else:
+        stored = applied = sum(int(b.size) for b in A.blocks)
+    nin = A.size[1] if op == "N" else A.size[0]
+    nout = A.size[0] if op == "N" else A.size[1]
+    return {"bytes": float(stored * s + (nin + nout) * s * nrhs),
+            "flops": (8.0 if np.dtype(A.dtype).kind == "c" else 2.0) * applied * nrhs}
+
+
+def c2_whole_job_work(spec, scattered=False):
+    from bsm_b200 import generators as G
+    S = G.NearfieldStructure(2, spec["n"], 20, 200, 6, scattered=scattered)
+    sz = S.sizes.astype(np.int64)
+    d = int((sz * sz).sum())
+    o = sum(int(sz[i]) * int(sz[S.near[i]].sum()) for i in range(1, S.nl))
+    return {"bytes": float((d + o) * 16 + 2 * spec["n"] * 16), "flops": 8.0 * (d + 2 * o)}
+
+
+def make_oracle(A, threads):
+    """Pre-marshalled C-oracle multiply of the host matrix: f(x, op) -> y (TEST INFRASTRUCTURE, CPU)."""
+    from helpers import to_oracle
+    from oracle import oracle_np as O
+    OA = to_oracle(A)
+    if isinstance(OA, O.OSBM):
+        C = O.CSbm(OA, threads)
+    elif isinstance(OA, O.OVBCRS):
+        C = O.CVbcrs(OA, threads)
+    else:
+        C = O.CBsm(OA, threads)
+    return lambda x, op: C.mul(x, op)
+
+
+def host_x(n, nrhs, dtype, seed=1234):
+    """The right-hand side every arm uses (NumPy, column-major n x nrhs, or a vector)."""
+    rng = np.random.default_rng(seed)
+    dt = np.dtype(dtype)
+    shape = (n,) if nrhs == 1 else (nrhs, n)
+    x = rng.standard_normal(shape)
+    if dt.kind == "c":
+        x = x + 1j * rng.standard_normal(shape)
+    x = x.astype(dt)
+    return x if nrhs == 1 else x.T       # (n, nrhs) view with column-major storage
 
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """NVML polled back to back from a thread while the timed region runs (the region lasts tens of ms: sleeping
+    between polls would leave a single sample)."""
 
     def __init__(self, index=0):
-        self.index = index
-        self.proc = None
-        self.lines = []
-        self.nvml = None
-        self.samples = []
+        self.index, self.samples, self.nvml, self._stop = index, [], None, True
 
     def _poll(self):
-        import pynvml as N
+        N = self.nvml
         h = N.nvmlDeviceGetHandleByIndex(self.index)
+        reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
         while not self._stop:
             try:
-                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
-                mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
-                rs = N.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(N, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((sm, mx, rs))
+                self.samples.append((N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), reasons(h)))
             except Exception:
-                pass
-            time.sleep(0.002)
+                time.sleep(0.001)
 
     def start(self):
-        # NVML polled in-process every ~2 ms (the timed region lasts tens of ms); nvidia-smi -lms as fallback
         try:
             import pynvml as N
             N.nvmlInit()
             self.nvml = N
+            self.sm_max = N.nvmlDeviceGetMaxClockInfo(N.nvmlDeviceGetHandleByIndex(self.index), N.NVML_CLOCK_SM)
             self._stop = False
             self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-            return
         except Exception:
             self.nvml = None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
 
     def stop(self):
-        if self.nvml is not None:
-            N = self.nvml
-            self._stop = True
-            self.thread.join(timeout=1.0)
-            names = {"hw_slowdown": getattr(N, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-                     "hw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-                     "sw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-                     "sw_power_cap": getattr(N, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-            reasons = sorted(k for k, bit in names.items() if any(r & bit for _, _, r in self.samples))
-            sm = [a for a, _, _ in self.samples]
-            mx = [b for _, b, _ in self.samples]
-            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                    "reasons": reasons, "samples": len(sm), "source": "nvml polled during the timed region"}
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [t.strip() for t in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        N = self.nvml
+        self._stop = True
+        self.thread.join(timeout=1.0)
+        names = {"hw_slowdown": getattr(N, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(N, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        sm = [a for a, _ in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.sm_max),
+                "reasons": sorted(k for k, bit in names.items() if any(r & bit for _, r in self.samples)),
+                "samples": len(sm), "source": "nvml polled back to back during the timed region"}
 
 
-# ----------------------------------------------------------------------------- CPU baseline (oracle)
-def cpu_sample(name, scale_hint, steps, warmup, min_seconds=8.0):
-    """Times the oracle (C restatement of the reference schedule, all host threads) on a bounded sample of
-    the workload. Returns (GB/s, cores, sample description, seconds per multiply)."""
-    import bsm_b200 as B
-    from bsm_b200 import _lib as L
-    from bsm_b200 import generators as G
-    from helpers import to_oracle
-    from oracle import oracle_np as O
-
-    threads = os.cpu_count() or 1
-    nrhs = 1
-    if name == "c2":
-        n = min(100_000, workload_spec(name, scale_hint)["n"])
-        A = G.symmetric_nearfield(seed=2, n=n, threads=min(threads, 16))
-        sample = f"same generator at N={n} (~{n / 1e6 * 12.7:.2f} GB ComplexF64), {threads} threads"
-        op = "N"
-    elif name == "c3":
-        n = min(1_000_000, workload_spec(name, scale_hint)["n"])
-        A = G.vbcrs_variable(seed=3, n=n, threads=min(threads, 16))
-        sample = f"same generator at {n} rows, {threads} threads"
-        op = "N"
-    elif name == "c1":
-        A = G.blocksparse_uniform(seed=1)
-        sample, op = f"full C1 matrix, {threads} threads", "N"
-    elif name == "c5":
-        A = G.blocksparse_uniform(seed=5, n=100_000 // 32 * 32, nblocks=20_000)
-        sample, op = f"same generator at N={A.size[0]}, 20000 blocks, 64 right-hand sides as a column loop, {threads} threads", "N"
-        nrhs = 64
-    else:
-        A = G.blocksparse_large(seed=4, grid=16)
-        sample, op = f"same generator on a 16x16 grid (13 blocks), {threads} threads", "T"
-    work = A.device(device=L.DEVICE_NONE).work(op, nrhs=nrhs)
-    OA = to_oracle(A)
-    rng = np.random.default_rng(0)
-    x = rng.standard_normal(A.size[1]).astype(A.dtype)
-    if isinstance(OA, O.OSBM):
-        C = O.CSbm(OA, threads)
-        run = lambda: C.mul(x, op)
-    elif isinstance(OA, O.OVBCRS):
-        run = lambda: O.c_mul_vbcrs(OA, x, op, threads=threads)
-    else:
-        run = lambda: O.c_mul_bsm(OA, x, op, threads=threads)
-    if nrhs > 1:      # LinearMaps applies a matrix right-hand side column by column
-        one = run
-        run = lambda: [one() for _ in range(nrhs)]
-    for _ in range(max(1, min(warmup, 2))):
+# ----------------------------------------------------------------------------- CPU arm (oracle)
+def cpu_time(run, steps, warmup, budget_s):
+    for _ in range(max(1, warmup)):
         run()
-    times = []
-    t_begin = time.perf_counter()
-    while len(times) < steps or (time.perf_counter() - t_begin) < min_seconds:
+    times, t_begin = [], time.perf_counter()
+    while len(times) < steps and (not times or time.perf_counter() - t_begin < budget_s):
         t0 = time.perf_counter()
         run()
         times.append(time.perf_counter() - t0)
-        if len(times) >= 200 or (time.perf_counter() - t_begin) > 30:
-            break
-    sec = float(np.median(times))
-    return work["bytes"] / sec / 1e9, threads, sample, sec, work["flops"] / sec / 1e9
+    return float(np.median(times)), len(times)
+
+
+def cpu_arm(name, scale, hard, A, steps, warmup, budget_s):
+    """Times the C oracle (all host threads) on the SAME matrix and x as the GPU arm. For c5 a step is a bounded
+    sample: 8 of the 64 right-hand sides (LinearMaps applies a matrix right-hand side column by column), and
+    the GB/s are those of the sample."""
+    spec = workload_spec(name, scale, hard)
+    threads = os.cpu_count() or 1
+    op, nrhs = spec["op"], spec.get("nrhs", 1)
+    ncols = min(nrhs, 8)
+    nin = A.size[1] if op == "N" else A.size[0]
+    x = host_x(nin, nrhs, A.dtype)
+    orc = make_oracle(A, threads)
+    if nrhs == 1:
+        run = lambda: orc(x, op)
+        sample = f"the full workload ({spec['desc']}), same x, {threads} threads"
+    else:
+        cols = [np.ascontiguousarray(x[:, j]) for j in range(ncols)]
+        run = lambda: [orc(c, op) for c in cols]
+        sample = f"the full matrix, {ncols} of the {nrhs} right-hand sides as a column loop, {threads} threads"
+    sec, done = cpu_time(run, steps, warmup, budget_s)
+    w = host_work(A, op, ncols if nrhs > 1 else 1)
+    return {"gbs": w["bytes"] / sec / 1e9, "gflops": w["flops"] / sec / 1e9, "cores": threads, "sample": sample,
+            "sec": sec, "steps_timed": done}
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    gbs, cores, sample, sec, gflops = cpu_sample(args.workload, args.scale, args.steps, args.warmup)
-    spec = workload_spec(args.workload, args.scale)
+    """--impl reference: the CPU restatement of the reference's own multiply (oracle port; the reference is Julia and
+    cannot be installed here) on the host cores, same config as the GPU arm. Rank 0 only; libbsm_b200.so is never
+    loaded by this arm."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    spec = workload_spec(args.workload, args.scale, args.hard)
+    A, _ = build_workload(args.workload, args.scale, 0, 1, threads=min(os.cpu_count() or 8, 32), hard=args.hard)
+    r = cpu_arm(args.workload, args.scale, args.hard, A, args.steps, args.warmup, budget_s=120.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": spec["dtype"], "data": "synthetic",
-        "gflops": gflops,
-        "config": {"workload": spec["desc"], "note": "CPU restatement of the reference schedule (oracle port); "
-                   "Julia is not installable in this image"},
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": r["gbs"], "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": r["steps_timed"], "warmup": args.warmup, "ms_per_step": r["sec"] * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": spec["dtype"], "data": "synthetic", "gflops": r["gflops"],
+        "config": {"workload": spec["desc"], "op": spec["op"],
+                   "note": "CPU restatement of the reference schedule (oracle port, kind=port): Julia is not installable "
+                           "in this image; " + r["sample"]},
+        "cpu_baseline": {"value": r["gbs"], "unit": "GB/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["gbs"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+    return 0
 
 
 # ----------------------------------------------------------------------------- B200 arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
-    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
-    ap.add_argument("--variant", type=int, default=0)
-    ap.add_argument("--xchg", default="peer", choices=["peer", "nccl"],
-                    help="N > 1, one right-hand side: peer = x read from its owners over NVLink inside the kernels "
-                         "(no collective); nccl = all-gather of x, then multiply")
-    ap.add_argument("--broadcasts", action="store_true", help="N > 1: grouped in-place broadcasts instead of the all-gather")
-    ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-gather, then multiply, on one stream")
-    ap.add_argument("--op", default=None, choices=["N", "T", "C"], help="override the workload's op (development)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-    if args.impl == "reference":
-        return run_reference(args)
+class Ctx:
+    pass
 
+
+def dgemm_peak(torch, dev):
+    a64 = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    b64 = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        torch.matmul(a64, b64)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    best = 1e9
+    for _ in range(5):
+        ev[0].record()
+        torch.matmul(a64, b64)
+        ev[1].record()
+        torch.cuda.synchronize()
+        best = min(best, ev[0].elapsed_time(ev[1]))
+    return 2 * 4096 ** 3 / (best * 1e-3) / 1e12
+
+
+def run_workload(cx, name, primary):
+    """One workload on the B200 arm. Returns the JSON line (rank 0) or None (other ranks); raises on parity failure
+    only after the line was built (the caller prints it, then exits non-zero)."""
     import torch
     import torch.distributed as dist
     import bsm_b200 as B
     from bsm_b200 import _lib as L
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    spec = workload_spec(args.workload, args.scale)
-
-    t0 = time.time()
-    host_threads = max(1, (os.cpu_count() or 8) // max(world, 1))
-    A, op, own, rb = build_workload(args.workload, args.scale, rank, world, threads=min(host_threads, 32))
-    if args.op:
-        op = args.op
-    t_gen = time.time() - t0
-    t0 = time.time()
-    full_work = None
-    if world > 1:
-        # one process per GPU: nnz-balanced block-row slabs, libbsm_b200's own NCCL communicator
-        from bsm_b200.dist import Comm, SlabMatrix
-        comm = Comm.from_torch(local)
-        comm.set_overlap(not args.no_overlap)
-        comm.set_collective(args.broadcasts)
-        if rb is None:        # generic partition of the full host matrix (every rank generated it)
-            full_work = A.device(device=L.DEVICE_NONE).work(op, nrhs=spec.get("nrhs", 1))
-            SM = SlabMatrix(A, comm, ops=(op,), variant=args.variant)
-        else:                 # c2: every rank generated only its slab's blocks
-            SM = SlabMatrix(A, comm, cuts=rb, variant=args.variant)
-        D, own, rb = SM.local, SM.own, SM.cuts
-    else:
-        D = B.DeviceMatrix(A, device=local, variant=args.variant)
-    torch.cuda.synchronize()
-    t_pack = time.time() - t0
-    tdt = {"c128": torch.complex128, "f64": torch.float64, "f32": torch.float32}[spec["dtype"]]
-    nin = A.size[1] if op == "N" else A.size[0]
-    nout = A.size[0] if op == "N" else A.size[1]
+    args, rank, world, local, dev = cx.args, cx.rank, cx.world, cx.local, cx.dev
+    hard = args.hard if name == "c2" else ""
+    spec = workload_spec(name, args.scale, hard)
+    op = args.op or spec["op"]
     nrhs = spec.get("nrhs", 1)
-    work = D.work(op, nrhs=nrhs)
-    if world > 1 and full_work is not None:
-        work = full_work
-    elif world > 1:
-        # whole-job algorithmic bytes: every stored entry once (slabs duplicate boundary blocks, that is
-        # overhead, not work) — computed from the structure on rank 0's formula for the full matrix
-        from bsm_b200 import generators as G
-        S = G.NearfieldStructure(2, spec["n"], 20, 200, 6)
-        sz = S.sizes.astype(np.int64)
-        stored = int((sz * sz).sum() + sum(int(sz[i]) * int(sz[S.near[i]].sum()) for i in range(1, S.nl)))
-        work = {"bytes": stored * 16.0 + 2 * spec["n"] * 16.0, "flops": 8.0 * (2 * stored - int((sz * sz).sum())),
-                "index_table_bytes": 0.0}
-
-    g = torch.Generator(device="cpu").manual_seed(1234)
-    if nrhs == 1:
-        x_host = torch.randn(nin, dtype=tdt, generator=g).pin_memory()
-        y_host = torch.empty(nout, dtype=tdt).pin_memory()
-        y_dev = torch.zeros(nout, dtype=tdt, device=dev)
-    else:   # column-major (nin x nrhs) / (nout x nrhs)
-        x_host = torch.randn((nrhs, nin), dtype=tdt, generator=g).pin_memory().t()
-        y_host = torch.empty((nrhs, nout), dtype=tdt).pin_memory().t()
-        y_dev = torch.zeros((nrhs, nout), dtype=tdt, device=dev).t()
-    x_full = x_host.to(dev) if nrhs == 1 else x_host.t().to(dev).t()
-
-    peer = world > 1 and nrhs == 1 and args.xchg == "peer"
-    if peer:
-        try:
-            xs = comm.alloc(nin, np.dtype({"c128": np.complex128, "f64": np.float64, "f32": np.float32}[spec["dtype"]]))
-            xs.copy_(x_full)
-            ok = 1
-        except Exception as exc:       # no peer access between the GPUs of this box: NCCL path
-            print(f"[rank {rank}] peer mode unavailable ({exc}); falling back to the NCCL all-gather", file=sys.stderr)
-            ok = 0
-        t_ok = torch.tensor([ok], device=dev)
-        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)
-        peer = bool(t_ok.item())
-    if peer:
-        x_full = xs
-
-        def step():
-            SM.mul_peer(op, x_full, y_dev)   # bsm_mul_dist_peer: flag barrier, multiply reading x over NVLink, flag barrier
-    elif world > 1:
-        def step():
-            SM.mul(op, x_full, y_dev)   # bsm_mul_dist: NCCL all-gather of the x slabs (in place), then the slab multiply
-    else:
-        def step():
-            D.mul(op, x_full, y_dev)
+    npdt = np.dtype(NPDT[spec["dtype"]])
+    tdt = {"c128": torch.complex128, "f64": torch.float64, "f32": torch.float32}[spec["dtype"]]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    barrier()          # ranks finish generating / packing at different times
+    t0 = time.time()
+    host_threads = max(1, (os.cpu_count() or 8) // max(world, 1))
+    A, rb = build_workload(name, args.scale, rank, world, threads=min(host_threads, 32), hard=hard)
+    t_gen = time.time() - t0
+    nin = A.size[1] if op == "N" else A.size[0]
+    nout = A.size[0] if op == "N" else A.size[1]
+    rhs_split = world > 1 and nrhs > 1          # c5 on N GPUs: columns split, A replicated, no exchange
+    if rhs_split and nrhs % world:
+        raise SystemExit("the right-hand sides must divide evenly among the ranks")
+
+    t0 = time.time()
+    SM = comm = None
+    if world > 1 and not rhs_split:
+        from bsm_b200.dist import SlabMatrix
+        comm = cx.comm
+        if rb is None:        # generic partition of the full host matrix (every rank generated it)
+            SM = SlabMatrix(A, comm, ops=(op,), variant=args.variant)
+        else:                 # c2: every rank generated only its slab's blocks
+            SM = SlabMatrix(A, comm, cuts=rb, variant=args.variant)
+        D, own = SM.local, SM.own
+        work = c2_whole_job_work(spec, "scattered" in hard) if rb is not None else host_work(A, op, nrhs)
+    else:
+        D = B.DeviceMatrix(A, device=local, variant=args.variant)
+        own = (0, nout)
+        work = host_work(A, op, nrhs)
+    torch.cuda.synchronize()
+    t_pack = time.time() - t0
+
+    # ---- operands: the same x on every arm and every rank
+    xh = host_x(nin, nrhs, npdt)
+    j0, j1 = (rank * (nrhs // world), (rank + 1) * (nrhs // world)) if rhs_split else (0, nrhs)
+    if nrhs == 1:
+        x_full = torch.from_numpy(xh).to(dev)
+        y_dev = torch.zeros(nout, dtype=tdt, device=dev)
+    else:                     # this rank's column group, column-major
+        x_full = torch.from_numpy(np.ascontiguousarray(xh[:, j0:j1].T)).to(dev).t()
+        y_dev = torch.zeros((j1 - j0, nout), dtype=tdt, device=dev).t()
+    peer = SM is not None and nrhs == 1 and args.xchg == "peer"
+    if peer:
+        xs = comm.alloc(nin, npdt)
+        xs.copy_(x_full)
+        x_full = xs
+        step = lambda: SM.mul_peer(op, x_full, y_dev)
+    elif SM is not None:
+        step = lambda: SM.mul(op, x_full, y_dev)   # bsm_mul_dist: NCCL all-gather of the x slabs, then the slab multiply
+    else:
+        step = lambda: D.mul(op, x_full, y_dev)
+
+    barrier()
     for _ in range(args.warmup):
         step()
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l2_resident = work["bytes"] <= 4 * 126e6
-    barrier()
-    # single GPU: the per-kernel event brackets (bsm_set_profiling, a ring of 64 triples inside bsm_mul) are
-    # recorded IN the timed region, so roofline.achieved is the dominant kernel's average over these very steps
-    inline_prof = world == 1 and not l2_resident
-    k_ms = f_ms = None
+    inline_prof = not l2_resident
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if inline_prof:
-        D.set_profiling(True)
+        D.set_profiling(True)     # per-kernel event brackets inside bsm_mul, recorded IN the timed region
+    barrier()
+    if rank == 0 and primary:
+        sampler.start()
     if not l2_resident:
         e0.record()
         for _ in range(args.steps):
@@ -390,9 +362,6 @@ def main():
         e1.record()
         barrier()
         ms_total = e0.elapsed_time(e1)
-        if inline_prof:
-            k_ms, f_ms = D.profile()
-            D.set_profiling(False)
     else:
         # working set fits the 126 MB L2: flush it (256 MB write) before every timed iteration and time each
         # multiply with its own pair of events, so the blocks really come from HBM
@@ -405,83 +374,116 @@ def main():
             b.record()
         barrier()
         ms_total = float(sum(a.elapsed_time(b) for a, b in evs))
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and primary) else None
+    if inline_prof:
+        k_ms, f_ms = D.profile()
+        D.set_profiling(False)
+    else:
+        D.set_profiling(True)
+        ks, fs = [], []
+        for _ in range(max(5, min(args.steps, 20))):
+            flush.zero_()
+            step()
+            a, b = D.profile()
+            ks.append(a)
+            fs.append(b)
+        D.set_profiling(False)
+        k_ms, f_ms = float(np.mean(ks)), float(np.mean(fs))
     if world > 1:
-        t = torch.tensor([ms_total], device=dev)
+        t = torch.tensor([ms_total, k_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+        ms_total, k_ms_max = float(t[0].item()), float(t[1].item())
+    else:
+        k_ms_max = k_ms
     ms_step = ms_total / args.steps
 
-    # per-kernel device time of the dominant kernel (CUDA events inside bsm_mul, same stream); N > 1 and the
-    # L2-flushed small case measure it in a separate loop on the rank-local handle
-    D.set_profiling(True)
-    main_ms, fin_ms = [], []
-    for _ in range(0 if inline_prof else max(5, min(args.steps, 20))):
-        # the events of the LAST multiply of a back-to-back burst: the kernel is timed in steady state (clocks up,
-        # no host synchronisation in front of it), like the steps of the timed region
-        for k in range(1 if l2_resident else 4):
-            if l2_resident:
-                flush.zero_()
-            D.mul(op, x_full, y_dev)
-        a, b = D.profile()
-        main_ms.append(a)
-        fin_ms.append(b)
-    D.set_profiling(False)
-    if not inline_prof:
-        k_ms, f_ms = float(np.mean(main_ms)), float(np.mean(fin_ms))
-    fin_ms = [f_ms]
-    local_work = D.work(op, nrhs=nrhs)
-
-    # end to end through the host-pointer C-ABI call: pinned host x → H2D → multiply → D2H → host y
-    e2e = None
-    if world == 1:
-        xh, yh = (x_host.numpy(), y_host.numpy()) if nrhs == 1 else (x_host.t().numpy().T, y_host.t().numpy().T)
-        for _ in range(2):
-            D.mul(op, xh, yh)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            D.mul(op, xh, yh)
-        e2e_s = (time.perf_counter() - t0) / args.steps
-        e2e = {"value": work["bytes"] / e2e_s / 1e9, "unit": "GB/s", "ms_per_step": e2e_s * 1e3,
-               "h2d_bytes_per_step": int(x_host.numel() * x_host.element_size()),
-               "d2h_bytes_per_step": int(y_host.numel() * y_host.element_size())}
+    # ---- parity at the benchmarked size: this rank's y slice against the C oracle on the same matrix and x
+    y_dev.zero_()
+    step()
+    torch.cuda.synchronize()
+    tol = TOL[spec["dtype"]]
+    orc = make_oracle(A, host_threads)
+    if nrhs == 1:
+        yo = orc(xh, op)[own[0]:own[1]]
+        yg = y_dev[own[0]:own[1]].cpu().numpy()
+        if npdt == np.float32:      # the 1e-5 bound is against a Float64 evaluation
+            from helpers import oracle_mul
+            yo = oracle_mul(A, xh, op, threads=host_threads, f64=True)[own[0]:own[1]]
+        err = float(np.linalg.norm(yg.astype(np.complex128) - yo) / max(np.linalg.norm(yo), 1e-300))
+        checked = f"rows {own[0]}:{own[1]} of y" if world > 1 else "all of y"
     else:
-        # N > 1: each rank copies its x slice in and its y slice out every step
-        rows = own[1] - own[0]
+        pc = list(range(j0, j1))[:: max(1, (j1 - j0) // 4)][:4]       # up to 4 of this rank's columns
+        yg = y_dev.t().cpu().numpy()
+        num = den = 0.0
+        for j in pc:
+            yo = orc(np.ascontiguousarray(xh[:, j]), op)
+            num += float(np.linalg.norm(yg[j - j0] - yo) ** 2)
+            den += float(np.linalg.norm(yo) ** 2)
+        err = float(np.sqrt(num / max(den, 1e-300)))
+        checked = f"columns {pc} of Y"
+    del orc
+    if world > 1:
+        t = torch.tensor([err], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        err = float(t.item())
+    parity = {"rel_err": err, "tol": tol, "op": op, "ok": bool(err <= tol),
+              "checked": f"{checked} on every rank vs the C oracle (oracle/) on the same full-size matrix and x; max over ranks"}
+
+    # ---- end to end through the host-pointer C-ABI call: pinned host x -> H2D -> multiply -> D2H -> host y
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+    if SM is None:
         if nrhs == 1:
-            xs_h = x_host[own[0]:own[1]].clone().pin_memory()
-            ys_h = torch.empty(rows, dtype=tdt).pin_memory()
-        else:   # slab rows of all columns: contiguous pinned buffers, strided placement done on the device
-            xs_h = x_host[own[0]:own[1]].t().contiguous().pin_memory()
-            ys_h = torch.empty((nrhs, rows), dtype=tdt).pin_memory()
-            xs_d, ys_d = torch.empty_like(xs_h, device=dev), torch.empty_like(ys_h, device=dev)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            if nrhs == 1:
-                x_full[own[0]:own[1]].copy_(xs_h, non_blocking=True)
-            else:
-                xs_d.copy_(xs_h, non_blocking=True)
-                x_full[own[0]:own[1]].copy_(xs_d.t())
+            xt, xa = pinned(xh)
+            yt, ya = pinned(np.empty(nout, npdt))
+            run_e2e = lambda: D.mul(op, xa, ya)
+        else:
+            xt, xa = pinned(xh[:, j0:j1].T)
+            yt, ya = pinned(np.empty((j1 - j0, nout), npdt))
+            run_e2e = lambda: D.mul(op, xa.T, ya.T)
+        h2d, d2h = nin * nrhs * npdt.itemsize, nout * nrhs * npdt.itemsize
+    elif peer:
+        xt, xa = pinned(xh[own[0]:own[1]])
+        yt, ya = pinned(np.empty(own[1] - own[0], npdt))
+        run_e2e = lambda: SM.mul_peer_host(op, xa, x_full, y_dev, ya)
+        h2d, d2h = nin * npdt.itemsize, nout * npdt.itemsize
+    else:
+        xt, xa = pinned(xh[own[0]:own[1]])
+        yt = torch.empty(own[1] - own[0], dtype=tdt).pin_memory()
+
+        def run_e2e():
+            x_full[own[0]:own[1]].copy_(xt, non_blocking=True)
             step()
-            if nrhs == 1:
-                ys_h.copy_(y_dev[own[0]:own[1]], non_blocking=True)
-            else:
-                ys_d.copy_(y_dev[own[0]:own[1]].t())
-                ys_h.copy_(ys_d, non_blocking=True)
+            yt.copy_(y_dev[own[0]:own[1]], non_blocking=True)
             torch.cuda.synchronize()
-        barrier()
-        t = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
+        h2d, d2h = nin * npdt.itemsize, nout * npdt.itemsize
+    for _ in range(2):
+        run_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run_e2e()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-        e2e = {"value": work["bytes"] / e2e_s / 1e9, "unit": "GB/s", "ms_per_step": e2e_s * 1e3,
-               "h2d_bytes_per_step": int(nin * nrhs * x_host.element_size()),
-               "d2h_bytes_per_step": int(nout * nrhs * y_host.element_size())}
+    e2e = {"value": work["bytes"] / e2e_s / 1e9, "unit": "GB/s", "ms_per_step": e2e_s * 1e3,
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "call": "bsm_mul_host" if SM is None else ("bsm_mul_dist_peer_host" if peer else "torch copies + bsm_mul_dist")}
 
+    local_work = host_work(A, op, j1 - j0) if nrhs > 1 else host_work(A, op, 1)
+    if SM is not None:      # this rank's slab: what its kernel streams
+        lw = D.work(op, nrhs=1)
+        local_work = {"bytes": lw["bytes"] - lw["index_table_bytes"], "flops": lw["flops"]}
+    stats = D.plan_stats(op)
+    launches = D.launch_count(op)
+    if peer:
+        torch.cuda.synchronize()
+        comm.free(xs)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None, parity["ok"]
 
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     if peaks_file.exists():
@@ -489,36 +491,32 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = local_work["bytes"] / (k_ms * 1e-3) / 1e9
-    stats = D.plan_stats(op)
     kernel_name = max(stats["bytes"], key=stats["bytes"].get)
     if kernel_name == "sym_fused_tma_kernel" and args.variant == 2:
         kernel_name = "sym_fused_kernel"
     tensor = None
     if nrhs >= 8 and stats["spmm"] and args.variant != 1:
-        kernel_name = "spmm_dmma_kernel"
-        # FP64 tensor-pipe denominator: cuBLAS DGEMM measured here (MEASURED_PEAKS.json holds no FP64 figure)
-        a64 = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
-        b64 = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
-        for _ in range(2):
-            torch.matmul(a64, b64)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        best = 1e9
-        for _ in range(5):
-            ev[0].record()
-            torch.matmul(a64, b64)
-            ev[1].record()
-            torch.cuda.synchronize()
-            best = min(best, ev[0].elapsed_time(ev[1]))
-        dgemm_tf = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
+        kernel_name = stats.get("spmm_kernel", "spmm_dmma_kernel")
+        dgemm_tf = dgemm_peak(torch, dev)
         ach_tf = local_work["flops"] / (k_ms * 1e-3) / 1e12
         tensor = {"bound": "tensor", "achieved": ach_tf, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": ach_tf / dgemm_tf,
                   "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (best of 5)"}
+        launches = 1
     traffic = None
     tfile = ROOT / "profiles" / "traffic.json"
-    if tfile.exists() and args.scale == 1.0 and world == 1 and args.variant == 0 and not args.op:
-        ent = json.loads(tfile.read_text()).get(args.workload)
+    if tfile.exists() and args.scale == 1.0 and world == 1 and args.variant == 0 and not args.op and not hard:
+        ent = json.loads(tfile.read_text()).get(name)
         if ent and ent["kernel"] == kernel_name:
             traffic = ent["dram_bytes_per_launch"]     # dram__bytes_read.sum + write.sum, ncu --set full (profiles/)
+    if world == 1:
+        par = "single GPU"
+    elif rhs_split:
+        par = f"{nrhs} right-hand sides split x{world} ({nrhs // world} per rank), A replicated on every rank, no exchange"
+    elif peer:
+        par = (f"block-row slabs x{world}, x sharded in peer-mapped arrays, fetched from its owners over NVLink inside "
+               "the multiply kernels, both barriers inside the kernels (no collective, no extra launch)")
+    else:
+        par = f"block-row slabs x{world}, NCCL all-gather of x ({'sequential' if args.no_overlap else 'overlapped with the rank-local slices'})"
     line = {
         "metric": METRIC, "value": work["bytes"] / (ms_step * 1e-3) / 1e9, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -528,31 +526,102 @@ def main():
                    if not l2_resident else "working set fits L2: L2 flushed (256 MB write) before every timed iteration, "
                                            "each multiply timed by its own CUDA events",
                    "variant": {0: "auto", 1: "gather", 2: "fused", 3: "color", 4: "fused_tma"}[args.variant],
-                   "parallelism": (f"block-row slabs x{world}, " +
-                                   ("x read from its owners' peer-mapped arrays over NVLink inside the kernels (no collective)"
-                                    if peer else f"NCCL all-gather of x ({'sequential' if args.no_overlap else 'overlapped with the rank-local slices'})"))
-                   if world > 1 else "single GPU",
-                   "algorithmic_bytes": work["bytes"], "flops": work["flops"],
+                   "parallelism": par, "algorithmic_bytes": work["bytes"], "flops": work["flops"],
                    "gen_s": round(t_gen, 1), "pack_s": round(t_pack, 1), "plan": stats},
+        "parity": parity,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms,
-                     "finalize_ms": float(np.mean(fin_ms)), "peak_source": peak_src,
-                     "bytes_per_launch": local_work["bytes"]},
+                     "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms, "kernel_ms_max_over_ranks": k_ms_max,
+                     "finalize_ms": f_ms, "peak_source": peak_src, "bytes_per_launch": local_work["bytes"]},
         "e2e": e2e,
-        # our kernels per step: the multiply's own launches (+ the four flag-barrier kernels of peer mode)
-        "gpu_launches": int(args.steps * ((D.launch_count(op) if nrhs == 1 or tensor is None else 1) + (4 if peer else 0))),
+        "gpu_launches": int(args.steps * launches),
         "clocks": clocks,
     }
     if tensor is not None:
         line["roofline_tensor"] = tensor
-    if world == 1 and not args.no_cpu_baseline:
-        gbs, cores, sample, sec, gflops = cpu_sample(args.workload, args.scale, 3, 1)
-        line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample,
-                                "ms_per_multiply": sec * 1e3}
-    print(json.dumps(line))
-    if world > 1:
+    if world == 1 and primary and not args.no_cpu_baseline:
+        r = cpu_arm(name, args.scale, hard, A, 3, 1, budget_s=20.0)
+        line["cpu_baseline"] = {"value": r["gbs"], "unit": "GB/s", "cores": r["cores"], "kind": "port",
+                                "sample": r["sample"], "ms_per_multiply": r["sec"] * 1e3}
+    return line, parity["ok"]
+
+
+def compact(line):
+    keep = ("value", "unit", "n_gpus", "ms_per_step", "gflops", "dtype", "parity", "e2e", "gpu_launches")
+    out = {k: line[k] for k in keep if k in line}
+    out["workload"] = line["config"]["workload"]
+    out["parallelism"] = line["config"]["parallelism"]
+    out["roofline"] = {k: line["roofline"][k] for k in ("achieved", "peak", "frac", "kernel", "kernel_ms")}
+    if "roofline_tensor" in line:
+        out["roofline_tensor"] = {k: line["roofline_tensor"][k] for k in ("achieved", "peak", "frac")}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
+    ap.add_argument("--hard", default="", choices=["", "permuted", "scattered", "permuted+scattered"],
+                    help="c2 only: arbitrary unsorted index vectors and / or near leaves drawn from the whole leaf range")
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--xchg", default="peer", choices=["peer", "nccl"],
+                    help="N > 1, one right-hand side: peer = x read from its owners over NVLink inside the kernels "
+                         "(no collective); nccl = all-gather of x, then multiply")
+    ap.add_argument("--broadcasts", action="store_true", help="N > 1: grouped in-place broadcasts instead of the all-gather")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-gather, then multiply, on one stream")
+    ap.add_argument("--op", default=None, choices=["N", "T", "C"], help="override the workload's op (development)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="default workload only: skip the c3 / c5 companion results")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    cx = Ctx()
+    cx.args = args
+    cx.rank = int(os.environ.get("RANK", "0"))
+    cx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    cx.local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(cx.local)
+    cx.dev = torch.device("cuda", cx.local)
+    cx.comm = None
+    if cx.world > 1:
+        dist.init_process_group("nccl", device_id=cx.dev)
+        from bsm_b200.dist import Comm
+        cx.comm = Comm.from_torch(cx.local)     # libbsm_b200's own communicator (peer-mapped arrays, NCCL by dlopen)
+        cx.comm.set_overlap(not args.no_overlap)
+        cx.comm.set_collective(args.broadcasts)
+
+    names = [args.workload]
+    if args.workload == "c2" and not args.no_also and not args.hard and args.scale == 1.0 and not args.op and args.variant == 0:
+        names += list(ALSO)
+    lines, ok = [], True
+    for i, nm in enumerate(names):
+        line, good = run_workload(cx, nm, primary=(i == 0))
+        ok = ok and good
+        lines.append(line)
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+    if cx.rank == 0:
+        line = lines[0]
+        if len(lines) > 1:
+            line["also"] = [compact(l) for l in lines[1:]]
+        print(json.dumps(line))
+    if cx.world > 1:
         dist.destroy_process_group()
+    if not ok:
+        print("PARITY FAILURE: a GPU result differs from the oracle beyond the tolerance", file=sys.stderr)
+        return 1
+    return 0
 
 
 if __name__ == "__main__":
-    main()
+    sys.exit(main())

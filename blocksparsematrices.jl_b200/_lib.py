@@ -81,6 +81,8 @@ SIGNATURES = [
     ("bsm_dist_free", c_int, [c_void_p, c_void_p]),
     ("bsm_mul_dist_peer", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, _P64,
                                   c_void_p]),
+    ("bsm_mul_dist_peer_host", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, _P64, c_int64, c_int64, c_void_p]),
     ("bsm_mul_dist", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p,
                              c_int64, c_int64, _P64, c_void_p]),
     ("bsm_device_count", c_int, [POINTER(c_int)]),

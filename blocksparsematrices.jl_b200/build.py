@@ -41,17 +41,38 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compiles every source to an object file (in parallel, only the stale ones) and links the shared library."""
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", str(LIB), *[str(CSRC / f) for f in SOURCES]]
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = HERE / "_obj"
+    objdir.mkdir(exist_ok=True)
+    newest_dep = max((CSRC / f).stat().st_mtime for f in DEPS)
+    flags = [f for f in NVCC_FLAGS if f not in ("-shared", "-ldl")]
+
+    def compile_one(src):
+        obj = objdir / (Path(src).stem + ".o")
+        stamp = max((CSRC / src).stat().st_mtime, newest_dep)
+        if not force and obj.exists() and obj.stat().st_mtime > stamp:
+            return obj, ""
+        cmd = [nvcc_path(), *flags, "-c"]
+        if verbose:
+            cmd += ["-Xptxas", "-v"]
+        cmd += ["-o", str(obj), str(CSRC / src)]
+        res = subprocess.run(cmd, cwd=str(CSRC), capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        return obj, res.stdout + res.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB),
+           *[str(o) for o, _ in results], "-ldl", "-lpthread"]
     res = subprocess.run(cmd, cwd=str(CSRC), capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stdout + res.stderr)
+        print("".join(log for _, log in results))
     return LIB
 
 

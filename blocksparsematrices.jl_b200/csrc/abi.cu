@@ -104,6 +104,11 @@ struct bsm_matrix {
     // sparse(A) result built by bsm_sparse_build (sparse.cu), device arrays
     void *sparse_slot[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool restricted = false;
+    // partial-sum scratch: one persistent buffer per launch stream (sized for the largest plan), so that a multiply
+    // allocates nothing and concurrent multiplies on different streams never share partial sums
+    std::mutex scratch_mu;
+    std::vector<std::pair<cudaStream_t, void *>> scratch_by_stream;
+    size_t scratch_bytes = 0;
     // benchmarking: events around the kernels of the last bsm_mul
     bool profiling = false;
     // a ring of event triples: every bsm_mul while profiling is on records into the next slot, so a whole timed
@@ -155,8 +160,21 @@ int upload_arena(bsm_matrix *A) {
     }
     const int64_t stage_bytes = 64ll << 20;
     unsigned char *stage[2] = {nullptr, nullptr};
-    cudaEvent_t done[2];
-    cudaStream_t st;
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    cudaStream_t st = nullptr;
+    struct Cleanup {   // staging resources are released on every path out of this function
+        unsigned char **stage;
+        cudaEvent_t *done;
+        cudaStream_t *st;
+        ~Cleanup() {
+            if (*st) cudaStreamSynchronize(*st);
+            for (int i = 0; i < 2; ++i) {
+                if (stage[i]) cudaFreeHost(stage[i]);
+                if (done[i]) cudaEventDestroy(done[i]);
+            }
+            if (*st) cudaStreamDestroy(*st);
+        }
+    } cleanup{stage, done, &st};
     CUDA_TRY(cudaStreamCreate(&st));
     for (int i = 0; i < 2; ++i) {
         CUDA_TRY(cudaMallocHost((void **)&stage[i], (size_t)stage_bytes));
@@ -261,11 +279,6 @@ int upload_arena(bsm_matrix *A) {
     }
     if (int rc = flush()) return rc;
     CUDA_TRY(cudaStreamSynchronize(st));
-    for (int i = 0; i < 2; ++i) {
-        cudaFreeHost(stage[i]);
-        cudaEventDestroy(done[i]);
-    }
-    cudaStreamDestroy(st);
     return 0;
 }
 
@@ -340,14 +353,8 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
     // colour-ordered comparison variant: same contributions as the GATHER plans, launched colour by colour
     if (err.empty()) err = build_color_plan(H, ir[0], H.nrows, H.ncols, pp[0], H.plan[4]);
     if (err.empty()) err = build_color_plan(H, ir[1], H.ncols, H.nrows, pp[1], H.plan[5]);
-    // one-time setup of the stream-ordered pool the scratch vectors come from: keep freed memory cached
-    if (A->device != BSM_DEVICE_NONE) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, A->device) == cudaSuccess) {
-            uint64_t thr = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-    }
+    for (int p = 0; p < 4; ++p)
+        A->scratch_bytes = std::max(A->scratch_bytes, (size_t)H.plan[p].scratch_elems * (size_t)dtype_size(H.dtype));
     if (!err.empty()) {
         delete A;
         return fail(BSM_ERR_ARG, err);
@@ -384,6 +391,49 @@ int plan_index(const bsm_matrix *A, int op) {
     return base + (fused ? 2 : 0);
 }
 
+// Persistent partial-sum scratch of (handle, stream): allocated on the first multiply a stream sees.
+int get_scratch(bsm_matrix *A, cudaStream_t st, void **out) {
+    *out = nullptr;
+    if (A->scratch_bytes == 0) return 0;
+    std::lock_guard<std::mutex> lk(A->scratch_mu);
+    for (auto &e : A->scratch_by_stream)
+        if (e.first == st) {
+            *out = e.second;
+            return 0;
+        }
+    if (A->scratch_by_stream.size() >= 8) {   // streams come and go: recycle the oldest buffer (cudaFree waits for the device)
+        cudaFree(A->scratch_by_stream.front().second);
+        A->scratch_by_stream.erase(A->scratch_by_stream.begin());
+    }
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, A->scratch_bytes));
+    A->scratch_by_stream.emplace_back(st, p);
+    *out = p;
+    return 0;
+}
+
+// Dynamic shared-memory opt-in of every kernel instantiated for T, once per device (the attribute is per device).
+template <class T>
+int ensure_attrs(int device) {
+    static std::mutex mu;
+    static bool done[64] = {};
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[device & 63]) return 0;
+    CUDA_TRY(cudaFuncSetAttribute(sym_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fused_smem_bytes<T>()));
+    CUDA_TRY(cudaFuncSetAttribute(sym_fused_tma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fused_tma_smem_bytes<T>()));
+    CUDA_TRY(cudaFuncSetAttribute(sym_fused_tma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fused_tma_smem_bytes<T>()));
+    CUDA_TRY(cudaFuncSetAttribute(stream_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)stream_warp_smem_bytes<T>()));
+    if constexpr (sizeof(T) == 8)
+        CUDA_TRY(cudaFuncSetAttribute(spmm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)std::max(spmm_smem_bytes(true), spmm_smem_bytes(false))));
+    done[device & 63] = true;
+    return 0;
+}
+
 // phase 0: the whole multiply. Slab handles under bsm_mul_dist (nrhs = 1, scratch owned by the caller and passed
 // through *scratch_io): phase 1 = the slices whose inputs are rank-local (run while x is being all-gathered),
 // phase 2 = the remote slices (on a second stream, so the two grids fill each other's tails), phase 3 = the
@@ -406,26 +456,14 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
     const int32_t nwarp = (int32_t)HP.n_warp_slices;
     // the direct-load comparison kernel only knows whole segments with short T-form blocks
     const bool use_tma = A->variant != BSM_VARIANT_FUSED || HP.fused_general;
-    if (nfused > 0 || nwarp > 0) {
-        static bool attr_done_dev[64][3] = {};
-        const int di = sizeof(T) == 4 ? 0 : sizeof(T) == 8 ? 1 : 2;
-        bool &attr_done_ref = attr_done_dev[A->device & 63][di];
-        if (!attr_done_ref) {
-            CUDA_TRY(cudaFuncSetAttribute(sym_fused_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)fused_smem_bytes<T>()));
-            CUDA_TRY(cudaFuncSetAttribute(sym_fused_tma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)fused_tma_smem_bytes<T>()));
-            CUDA_TRY(cudaFuncSetAttribute(sym_fused_tma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)fused_tma_smem_bytes<T>()));
-            CUDA_TRY(cudaFuncSetAttribute(stream_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)stream_warp_smem_bytes<T>()));
-            attr_done_ref = true;
-        }
-    }
+    if (int rc = ensure_attrs<T>(A->device)) return rc;
     if (phase != 0)
         scratch = (T *)*scratch_io;
-    else if (HP.scratch_elems > 0)
-        CUDA_TRY(cudaMallocAsync((void **)&scratch, (size_t)HP.scratch_elems * sizeof(T), st));
+    else if (HP.scratch_elems > 0) {
+        void *sp = nullptr;
+        if (int rc = get_scratch(A, st, &sp)) return rc;
+        scratch = (T *)sp;
+    }
     // slice / item ranges of this phase
     const int32_t nitems_all = HP.witem_ptr.empty() ? 0 : (int32_t)HP.witem_ptr.size() - 1;
     const int32_t ngather_all = (int32_t)HP.slices.size() - nfused - nwarp;
@@ -493,12 +531,6 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
     if constexpr (sizeof(T) == 8) {
         // many right-hand sides: one pass over A on the FP64 tensor cores instead of nrhs SpMV passes
         if (nrhs >= kSpmmMinRhs && HP.spmm_ok && A->variant != BSM_VARIANT_GATHER && p >= 2) {
-            static bool spmm_attr = false;
-            if (!spmm_attr) {
-                CUDA_TRY(cudaFuncSetAttribute(spmm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)std::max(spmm_smem_bytes(true), spmm_smem_bytes(false))));
-                spmm_attr = true;
-            }
             SpmmArgs m;
             m.arena = (const double *)A->arena;
             m.contrib = DP.contrib.p;
@@ -549,10 +581,25 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
         a.pool = A->pool.p;
         a.x.x = x + j * ldx;
         a.x.npeer = 0;
+        // the last kernel that reads x runs the exit barrier of peer mode
+        const int last_kind = (g1 > g0) ? 2 : (w1 > w0) ? 1 : (f1 > f0) ? 0 : -1;
         if (px && px->npeer > 0) {   // peer mode (nrhs = 1): element i comes from its owner's array
             a.x.npeer = px->npeer;
             for (int r = 0; r < px->npeer; ++r) a.x.peer[r] = (const T *)px->peer[r];
             for (int r = 0; r <= px->npeer; ++r) a.x.cuts[r] = px->cuts[r];
+            a.x.sync.peer_flags = px->peer_flags;
+            a.x.sync.my_flags = px->my_flags;
+            a.x.sync.state = px->state;
+            a.x.sync.nranks = px->npeer;
+            a.x.sync.rank = px->rank;
+            a.x.sync.do_exit = 0;
+            a.x.sync.arrivals = 1;
+            if (last_kind < 0) {   // nothing to multiply on this rank: the barriers alone
+                PeerSync ps = a.x.sync;
+                ps.do_exit = 1;
+                peer_sync_kernel<<<1, 32, 0, st>>>(ps);
+                CUDA_TRY(cudaGetLastError());
+            }
         }
         a.y = y + j * ldy;
         a.scratch = scratch;
@@ -570,6 +617,10 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
         if (f1 > f0) {
             MulArgs<T> b = a;
             b.slices = a.slices + f0;
+            if (b.x.npeer && last_kind == 0) {
+                b.x.sync.do_exit = 1;
+                b.x.sync.arrivals = f1 - f0;
+            }
             if (use_tma)
                 if (HP.fused_general)
                     sym_fused_tma_kernel<T, true><<<f1 - f0, kPThreads, fused_tma_smem_bytes<T>(), st>>>(b);
@@ -593,6 +644,10 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             w.nitems = w1 - w0;
             w.beta_false = a.beta_false;
             w.conj = a.conj;
+            if (w.x.npeer && last_kind == 1) {
+                w.x.sync.do_exit = 1;
+                w.x.sync.arrivals = (int32_t)((w.nitems + kWWarps - 1) / kWWarps) * kWWarps;
+            }
             stream_warp_kernel<T><<<(unsigned)((w.nitems + kWWarps - 1) / kWWarps), kWWarps * 32,
                                     stream_warp_smem_bytes<T>(), st>>>(w);
             CUDA_TRY(cudaGetLastError());
@@ -601,6 +656,10 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             MulArgs<T> b = a;
             b.slices = a.slices + nfused + nwarp + g0;
             b.nslices = g1 - g0;
+            if (b.x.npeer) {
+                b.x.sync.do_exit = 1;
+                b.x.sync.arrivals = b.nslices;
+            }
             gather_gemv_kernel<T, VMAX><<<b.nslices, kThreads, 0, st>>>(b);
             CUDA_TRY(cudaGetLastError());
         }
@@ -627,7 +686,6 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             CUDA_TRY(cudaEventRecord(A->ev[2], st));
         }
     }
-    if (scratch && phase == 0) CUDA_TRY(cudaFreeAsync(scratch, st));
     return 0;
 }
 
@@ -908,6 +966,7 @@ int bsm_destroy(bsm_handle h) {
     for (int p = 0; p < 6; ++p) h->plan[p].release();
     if (h->hx) cudaFree(h->hx);
     if (h->hy) cudaFree(h->hy);
+    for (auto &e : h->scratch_by_stream) cudaFree(e.second);
     if (h->host_stream) cudaStreamDestroy(h->host_stream);
     for (cudaEvent_t e : h->ev_ring) cudaEventDestroy(e);
     delete h;
@@ -1019,6 +1078,11 @@ SparseResult *bsm_sparse_slot(bsm_handle h) {
     return R;
 }
 
+int bsm_get_scratch(bsm_handle h, void *stream, void **out) {
+    if (int rc = check_handle(h)) return rc;
+    DeviceGuard g(h->device);
+    return get_scratch(h, (cudaStream_t)stream, out);
+}
 int64_t bsm_plan_scratch_bytes(bsm_handle h, int op) {
     if (!h || op < BSM_OP_N || op > BSM_OP_C) return 0;
     return h->H.plan[plan_index(h, op)].scratch_elems * (int64_t)dtype_size(h->H.dtype);
@@ -1027,7 +1091,10 @@ int bsm_mul_phase(bsm_handle h, int op, const void *alpha, const void *beta, int
                   void *y_dev, void *stream, int phase, void **scratch_io, const PeerX *px) {
     if (int rc = check_handle(h)) return rc;
     if (h->device == BSM_DEVICE_NONE) return fail(BSM_ERR_CUDA, "host-only handle");
+    if (op < BSM_OP_N || op > BSM_OP_C) return fail(BSM_ERR_ARG, "bad op");
+    if (!alpha || (!beta && !beta_is_false) || !x_dev || !y_dev) return fail(BSM_ERR_ARG, "null argument");
     DeviceGuard g(h->device);
+    if (!g.ok) return fail(BSM_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = (cudaStream_t)stream;
     switch (h->H.dtype) {
     case BSM_F32:

@@ -80,6 +80,7 @@ void bsm_set_error(const std::string &msg);
 
 int bsm_plan_has_remote(bsm_handle h, int op);
 int64_t bsm_plan_scratch_bytes(bsm_handle h, int op);
+int bsm_get_scratch(bsm_handle h, void *stream, void **out);
 int bsm_mul_phase(bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false, const void *x_dev,
                   void *y_dev, void *stream, int phase, void **scratch_io, const bsm::PeerX *px);
 
@@ -102,7 +103,7 @@ struct bsm_comm_s {
     std::vector<Shared> shared;
     int32_t *flags = nullptr;               // this rank's flag array: ready[nranks], done[nranks]
     int32_t **peer_flags_dev = nullptr;     // device array: every rank's flag array
-    int32_t epoch = 0;
+    int32_t *sync_state = nullptr;          // local device words of the in-kernel barriers (kernels.cuh PeerSync)
 };
 
 namespace {
@@ -183,6 +184,7 @@ int bsm_dist_destroy(bsm_comm c) {
         if (sh.local) cudaFree(sh.local);
     }
     if (c->peer_flags_dev) cudaFree(c->peer_flags_dev);
+    if (c->sync_state) cudaFree(c->sync_state);
     if (c->stage) cudaFree(c->stage);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
@@ -229,13 +231,12 @@ int bsm_dist_allgather_rows(bsm_comm c, int dtype, void *x_dev, int64_t ldx, int
         const size_t chunk = (size_t)(maxrows * nrhs * s);
         const size_t need = chunk * (size_t)c->nranks;
         if (c->stage_bytes < need) {
-            for (auto &sh : c->shared) {
-        for (int p = 0; p < c->nranks; ++p)
-            if (p != c->rank && sh.peer[p]) cudaIpcCloseMemHandle(sh.peer[p]);
-        if (sh.local) cudaFree(sh.local);
-    }
-    if (c->peer_flags_dev) cudaFree(c->peer_flags_dev);
-    if (c->stage) cudaFree(c->stage);
+            // only the staging buffer is replaced; earlier collectives may still read it on either stream
+            if (c->stage) {
+                cudaStreamSynchronize(st);
+                cudaStreamSynchronize(c->comm_stream);
+                cudaFree(c->stage);
+            }
             c->stage = nullptr;
             c->stage_bytes = 0;
             if (cudaMalloc(&c->stage, need) != cudaSuccess) return dfail(BSM_ERR_ALLOC, "staging buffer of the all-gather");
@@ -284,35 +285,15 @@ int bsm_dist_set_collective(bsm_comm c, int use_broadcasts) {
 // ---- peer mode: x is read straight from its owners over NVLink -------------------------------------------
 namespace {
 
-// every rank tells every peer "my part of epoch `epoch` is finished" (which = 0: my x slab is written,
-// which = 1: I have finished reading x)
-__global__ void flag_signal_kernel(int32_t *const *peer_flags, int which, int rank, int nranks, int32_t epoch) {
-    const int p = threadIdx.x;
-    if (p >= nranks) return;
-    __threadfence_system();
-    *reinterpret_cast<volatile int32_t *>(peer_flags[p] + which * nranks + rank) = epoch;
-    __threadfence_system();
-}
-// ... and waits until every peer has said so
-__global__ void flag_wait_kernel(const int32_t *flags, int which, int nranks, int32_t epoch) {
-    const int p = threadIdx.x;
-    if (p >= nranks) return;
-    const volatile int32_t *f = flags + which * nranks + p;
-    const long long t0 = clock64();
-    while (*f < epoch) {
-        __nanosleep(100);
-        if (clock64() - t0 > 120000000000ll) __trap();   // ~60 s: a peer died or never entered the collective call
-    }
-    __threadfence_system();
-}
-
 // collective: cudaMalloc on every rank, IPC handles exchanged through the communicator, peers mapped
 int shared_alloc(bsm_comm c, size_t bytes, bsm_comm_s::Shared *out) {
     if (c->nranks > 8) return dfail(BSM_ERR_UNSUPPORTED, "peer mode supports up to 8 ranks");
     if (cudaSetDevice(c->device) != cudaSuccess) return dfail(BSM_ERR_CUDA, "cudaSetDevice failed");
     bsm_comm_s::Shared sh;
     if (cudaMalloc(&sh.local, bytes ? bytes : 16) != cudaSuccess) return dfail(BSM_ERR_ALLOC, "cudaMalloc of a peer-mapped array failed");
-    if (cudaMemset(sh.local, 0, bytes ? bytes : 16) != cudaSuccess) return dfail(BSM_ERR_CUDA, "cudaMemset failed");
+    // the zero fill must have landed before any peer can learn the handle (a peer's flag store must not be overwritten)
+    if (cudaMemset(sh.local, 0, bytes ? bytes : 16) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+        return dfail(BSM_ERR_CUDA, "cudaMemset failed");
     sh.peer[c->rank] = sh.local;
     if (c->nranks > 1) {
         cudaIpcMemHandle_t mine;
@@ -345,10 +326,14 @@ int ensure_flags(bsm_comm c) {
     if (c->flags) return 0;
     bsm_comm_s::Shared sh;
     if (int rc = shared_alloc(c, sizeof(int32_t) * 2 * (size_t)c->nranks, &sh)) return rc;
-    c->flags = (int32_t *)sh.local;
-    if (cudaMalloc(&c->peer_flags_dev, sizeof(int32_t *) * 8) != cudaSuccess) return dfail(BSM_ERR_ALLOC, "cudaMalloc failed");
-    cudaMemcpy(c->peer_flags_dev, sh.peer, sizeof(void *) * 8, cudaMemcpyHostToDevice);
     c->shared.push_back(sh);
+    if (cudaMalloc(&c->peer_flags_dev, sizeof(int32_t *) * 8) != cudaSuccess ||
+        cudaMalloc(&c->sync_state, sizeof(int32_t) * 4) != cudaSuccess)
+        return dfail(BSM_ERR_ALLOC, "cudaMalloc failed");
+    if (cudaMemcpy(c->peer_flags_dev, sh.peer, sizeof(void *) * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemset(c->sync_state, 0, sizeof(int32_t) * 4) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+        return dfail(BSM_ERR_CUDA, "initialising the barrier state failed");
+    c->flags = (int32_t *)sh.local;   // set last: a failed setup is retried, never half-used
     return 0;
 }
 
@@ -381,7 +366,11 @@ int bsm_dist_free(bsm_comm c, void *dev_ptr) {
 int bsm_mul_dist_peer(bsm_comm c, bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
                       void *x_shared, void *y_dev, const int64_t *in_cuts, void *stream) {
     if (!c || !h || !x_shared || !y_dev || !in_cuts) return dfail(BSM_ERR_ARG, "null argument");
+    if (op < BSM_OP_N || op > BSM_OP_C) return dfail(BSM_ERR_ARG, "bad op");
+    if (!alpha || (!beta && !beta_is_false)) return dfail(BSM_ERR_ARG, "alpha/beta is null");
     if (c->nranks == 1) return bsm_mul(h, op, alpha, beta, beta_is_false, x_shared, 0, y_dev, 0, 1, stream);
+    for (int p = 0; p < c->nranks; ++p)
+        if (in_cuts[p + 1] < in_cuts[p] || in_cuts[p + 1] >= (1ll << 31)) return dfail(BSM_ERR_ARG, "bad cuts");
     if (int rc = ensure_flags(c)) return rc;   // may grow c->shared: look x up afterwards
     const bsm_comm_s::Shared *sh = nullptr;
     for (const auto &s : c->shared)
@@ -394,17 +383,47 @@ int bsm_mul_dist_peer(bsm_comm c, bsm_handle h, int op, const void *alpha, const
         px.cuts[p] = (int32_t)in_cuts[p];
     }
     px.cuts[c->nranks] = (int32_t)in_cuts[c->nranks];
+    // The two barriers of a peer-mode multiply live INSIDE the multiply kernels (kernels.cuh PeerSync): "every x slab
+    // of this epoch is written" is signalled by the first CTA to start and awaited before the first x fetch; "every
+    // rank has finished reading" is signalled and awaited by the last CTA to finish — no extra launches. Nothing that
+    // can fail is left between the argument checks above and the launches, so a rank either enters the collective
+    // multiply or reports an error before any peer could wait on it.
+    px.peer_flags = c->peer_flags_dev;
+    px.my_flags = c->flags;
+    px.state = c->sync_state;
+    px.rank = c->rank;
+    void *scratch = nullptr;
+    return bsm_mul_phase(h, op, alpha, beta, beta_is_false, x_shared, y_dev, stream, 0, &scratch, &px);
+}
+
+int bsm_mul_dist_peer_host(bsm_comm c, bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
+                           const void *x_host_slab, void *x_shared, void *y_dev, void *y_host_slab,
+                           const int64_t *in_cuts, int64_t out_lo, int64_t out_hi, void *stream) {
+    if (!c || !h || !x_host_slab || !x_shared || !y_dev || !y_host_slab || !in_cuts)
+        return dfail(BSM_ERR_ARG, "null argument");
+    if (out_lo < 0 || out_hi < out_lo) return dfail(BSM_ERR_ARG, "bad output range");
+    const int dt = bsm_dtype_of(h);
+    if (dt < 0) return dfail(BSM_ERR_ARG, "bad handle");
+    const int64_t s = dt == BSM_F32 ? 4 : dt == BSM_F64 ? 8 : 16;
     cudaStream_t st = (cudaStream_t)stream;
-    const int32_t e = ++c->epoch;
-    // barrier 1: every rank's x slab of this epoch is written; then the multiply reads x where it lives;
-    // barrier 2: every rank has finished reading, so whatever follows on the stream may overwrite the slab
-    flag_signal_kernel<<<1, 32, 0, st>>>(c->peer_flags_dev, 0, c->rank, c->nranks, e);
-    flag_wait_kernel<<<1, 32, 0, st>>>(c->flags, 0, c->nranks, e);
-    void *unused = nullptr;
-    if (int rc = bsm_mul_phase(h, op, alpha, beta, beta_is_false, x_shared, y_dev, stream, 0, &unused, &px)) return rc;
-    flag_signal_kernel<<<1, 32, 0, st>>>(c->peer_flags_dev, 1, c->rank, c->nranks, e);
-    flag_wait_kernel<<<1, 32, 0, st>>>(c->flags, 1, c->nranks, e);
-    if (cudaGetLastError() != cudaSuccess) return dfail(BSM_ERR_CUDA, "flag kernels failed to launch");
+    if (cudaSetDevice(c->device) != cudaSuccess) return dfail(BSM_ERR_CUDA, "cudaSetDevice failed");
+    const int64_t lo = in_cuts[c->rank], hi = in_cuts[c->rank + 1];
+    // a failed copy must not keep this rank out of the collective multiply (the peers would wait for it): the
+    // error is remembered, the multiply still runs, and the failure is reported afterwards
+    cudaError_t e = cudaSuccess;
+    if (hi > lo)
+        e = cudaMemcpyAsync((unsigned char *)x_shared + lo * s, x_host_slab, (size_t)((hi - lo) * s), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && !beta_is_false && out_hi > out_lo)
+        e = cudaMemcpyAsync((unsigned char *)y_dev + out_lo * s, y_host_slab, (size_t)((out_hi - out_lo) * s),
+                            cudaMemcpyHostToDevice, st);
+    const int rc = bsm_mul_dist_peer(c, h, op, alpha, beta, beta_is_false, x_shared, y_dev, in_cuts, stream);
+    if (rc == 0 && e == cudaSuccess && out_hi > out_lo)
+        e = cudaMemcpyAsync(y_host_slab, (unsigned char *)y_dev + out_lo * s, (size_t)((out_hi - out_lo) * s),
+                            cudaMemcpyDeviceToHost, st);
+    const cudaError_t es = cudaStreamSynchronize(st);
+    if (rc != 0) return rc;
+    if (e != cudaSuccess || es != cudaSuccess)
+        return dfail(BSM_ERR_CUDA, std::string("host copies of the slab multiply: ") + cudaGetErrorString(e != cudaSuccess ? e : es));
     return 0;
 }
 
@@ -424,9 +443,7 @@ int bsm_mul_dist(bsm_comm c, bsm_handle h, int op, const void *alpha, const void
         // x slab run on the caller's stream; the remote slices and the gather pass follow the all-gather
         cudaStream_t st = (cudaStream_t)stream;
         void *scratch = nullptr;
-        const int64_t sbytes = bsm_plan_scratch_bytes(h, op);
-        if (sbytes > 0 && cudaMallocAsync(&scratch, (size_t)sbytes, st) != cudaSuccess)
-            return dfail(BSM_ERR_ALLOC, "scratch allocation failed");
+        if (int rc = bsm_get_scratch(h, stream, &scratch)) return rc;
         // x slab and scratch are ready at ev_ready: the all-gather (comm stream) and the remote slices (aux
         // stream, after the gather) hang off it, the local slices stay on the caller's stream
         if (cudaEventRecord(c->ev_ready, st) != cudaSuccess ||
@@ -443,7 +460,6 @@ int bsm_mul_dist(bsm_comm c, bsm_handle h, int op, const void *alpha, const void
             cudaStreamWaitEvent(st, c->ev_gathered, 0) != cudaSuccess)
             return dfail(BSM_ERR_CUDA, "event record/wait failed");
         if (int rc = bsm_mul_phase(h, op, alpha, beta, beta_is_false, x_dev, y_dev, stream, 3, &scratch, nullptr)) return rc;
-        if (scratch && cudaFreeAsync(scratch, st) != cudaSuccess) return dfail(BSM_ERR_CUDA, "scratch free failed");
         return 0;
     }
     if (c->nranks > 1) {

@@ -98,12 +98,66 @@ __device__ __forceinline__ Pack<T, V> load_stream(const T *p) {
 // peer-mapped memory but only its own slab [cuts[r], cuts[r+1]) is current; element i is read straight from
 // its owner's array over NVLink (npeer > 0), so the all-gather disappears into the kernels' own x fetches.
 constexpr int kMaxPeers = 8;
+
+// Peer-mode barriers folded into the multiply kernels (no extra launches). Every rank owns a flag array in
+// peer-mapped memory: ready[nranks] then done[nranks], written by the peers with the epoch (= index of the
+// multiply) they have reached. `state` are three words in LOCAL device memory: [0] epochs completed,
+// [1] epoch whose "ready" signal has been sent, [2] arrival counter of the exit barrier.
+//   entry  (every kernel of the multiply that reads x; one thread per CTA / warp, before the first x read):
+//          the first arrival tells every peer "my x slab of this epoch is written" (the kernel runs after the
+//          stream work that wrote it), then everybody waits until every peer has said so;
+//   exit   (the last x-reading kernel of the multiply; one thread per CTA / warp, after its last x read):
+//          the last arrival tells every peer "I have finished reading", waits until every peer has said so and
+//          publishes the epoch — the kernel cannot complete earlier, so whatever follows on the stream (the
+//          solver's update of the slab) is ordered after the peers' reads.
+struct PeerSync {
+    int32_t *const *peer_flags;
+    const int32_t *my_flags;
+    int32_t *state;
+    int32_t nranks, rank;
+    int32_t do_exit;      // this kernel runs the exit barrier
+    int32_t arrivals;     // arrivals the exit barrier expects
+};
+
+__device__ __forceinline__ void peer_spin(const int32_t *flag, int32_t epoch) {
+    const volatile int32_t *f = flag;
+    if (*f >= epoch) return;
+    const long long t0 = clock64();
+    while (*f < epoch) {
+        __nanosleep(64);
+        if (clock64() - t0 > 120000000000ll) __trap();   // ~60 s: a peer died or never entered the collective call
+    }
+}
+__device__ __forceinline__ void peer_entry(const PeerSync &s) {
+    const int32_t e = *reinterpret_cast<volatile int32_t *>(s.state) + 1;
+    if (atomicMax(s.state + 1, e) < e) {
+        __threadfence_system();
+        for (int p = 0; p < s.nranks; ++p) *reinterpret_cast<volatile int32_t *>(s.peer_flags[p] + s.rank) = e;
+    }
+    for (int p = 0; p < s.nranks; ++p) peer_spin(s.my_flags + p, e);
+    __threadfence_system();
+}
+__device__ __forceinline__ void peer_exit(const PeerSync &s) {
+    if (!s.do_exit) return;
+    __threadfence();
+    if (atomicAdd(s.state + 2, 1) != s.arrivals - 1) return;
+    const int32_t e = *reinterpret_cast<volatile int32_t *>(s.state) + 1;
+    __threadfence_system();
+    for (int p = 0; p < s.nranks; ++p)
+        *reinterpret_cast<volatile int32_t *>(s.peer_flags[p] + s.nranks + s.rank) = e;
+    for (int p = 0; p < s.nranks; ++p) peer_spin(s.my_flags + s.nranks + p, e);
+    *reinterpret_cast<volatile int32_t *>(s.state + 2) = 0;
+    *reinterpret_cast<volatile int32_t *>(s.state) = e;
+    __threadfence();
+}
+
 template <class T>
 struct XSrc {
     const T *x;
     const T *peer[kMaxPeers];
     int32_t cuts[kMaxPeers + 1];
     int32_t npeer;   // 0: plain array
+    PeerSync sync;   // npeer > 0 only
     __device__ __forceinline__ const T *ptr(int32_t i) const {
         if (npeer == 0) return x + i;
         int r = 0;
@@ -113,6 +167,14 @@ struct XSrc {
     }
     __device__ __forceinline__ T at(int32_t i) const { return *ptr(i); }
 };
+
+// the multiply of a rank whose slab holds no work: the barriers alone
+static __global__ void peer_sync_kernel(const PeerSync s) {
+    if (threadIdx.x == 0) {
+        peer_entry(s);
+        peer_exit(s);
+    }
+}
 
 // ---- kernel arguments ------------------------------------------------------------------------
 template <class T>
@@ -279,6 +341,10 @@ __global__ void __launch_bounds__(kThreads) gather_gemv_kernel(const MulArgs<T> 
     T *accT = reinterpret_cast<T *>(acc_raw);
     const bsm_slice sl = a.slices[blockIdx.x];
     const bool vec = (VMAX > 1) && (sl.flags & 2);
+    if (a.x.npeer) {
+        if (threadIdx.x == 0) peer_entry(a.x.sync);
+        __syncthreads();
+    }
     if (a.conj) {
         if (vec)
             slice_body<T, VMAX, true>(a, sl, xs, red, accT);
@@ -290,6 +356,7 @@ __global__ void __launch_bounds__(kThreads) gather_gemv_kernel(const MulArgs<T> 
         else
             slice_body<T, 1, false>(a, sl, xs, red, accT);
     }
+    if (a.x.npeer && threadIdx.x == 0) peer_exit(a.x.sync);   // every x read precedes the last barrier of slice_body
 }
 
 // ---- fused symmetric kernel ---------------------------------------------------------------------
@@ -411,6 +478,10 @@ __global__ void __launch_bounds__(kFThreads, 2) sym_fused_kernel(const MulArgs<T
     T *red = accT + kFMaxRows;  // [kFWarps][kFMaxRows]
     const bsm_slice sl = a.slices[blockIdx.x];
     const int32_t L = sl.r1;
+    if (a.x.npeer) {
+        if (threadIdx.x == 0) peer_entry(a.x.sync);
+        __syncthreads();
+    }
     if (a.conj) {
         if (L <= 64)
             fused_slice<T, 2, true>(a, sl, xs, xrs, red, accT);
@@ -426,6 +497,7 @@ __global__ void __launch_bounds__(kFThreads, 2) sym_fused_kernel(const MulArgs<T
         else
             fused_slice<T, 8, false>(a, sl, xs, xrs, red, accT);
     }
+    if (a.x.npeer && threadIdx.x == 0) peer_exit(a.x.sync);
 }
 
 template <class T>
@@ -723,6 +795,7 @@ __global__ void __launch_bounds__(kPThreads, 2) sym_fused_tma_kernel(const MulAr
             mbar_init(&empty[i], kFWarps);
         }
         mbar_fence_init();
+        if (a.x.npeer) peer_entry(a.x.sync);
     }
     __syncthreads();
     if (threadIdx.x >= kFThreads) {
@@ -745,6 +818,8 @@ __global__ void __launch_bounds__(kPThreads, 2) sym_fused_tma_kernel(const MulAr
         else
             tma_consumer<T, 8, false, GEN>(a, sl, stages, xs, xrs, accT, full, empty);
     }
+    // every x read of the consumers precedes the consumer barriers of the final reduction
+    if (a.x.npeer && threadIdx.x == 0) peer_exit(a.x.sync);
 }
 
 template <class T>
@@ -1105,26 +1180,36 @@ __global__ void __launch_bounds__(kWWarps * 32) stream_warp_kernel(const WarpArg
     extern __shared__ __align__(128) unsigned char wsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int32_t item = blockIdx.x * kWWarps + warp;
-    if (item >= a.nitems) return;
-    unsigned char *base = wsm + warp * stream_warp_smem_per_warp<T>();
-    unsigned char *ring = base;
-    const int4 *dring = reinterpret_cast<const int4 *>(base + kWRing);
-    T *xs = reinterpret_cast<T *>(base + kWRing + kWDSlots * kWDBatch * 32);
-    T *ts = xs + kWSegMax;
-    uint64_t *full = reinterpret_cast<uint64_t *>(ts + kWSegMax);
-    uint64_t *dbar = full + kWNB;
-    if (lane == 0) {
-        for (int i = 0; i < kWNB; ++i) mbar_init(&full[i], 33);  // lane 0's expect_tx + 32 cp.async arrivals
-        for (int i = 0; i < kWDSlots; ++i) mbar_init(&dbar[i], 1);
-        mbar_fence_init();
+    if (a.x.npeer) {   // every warp is its own pipeline: one arrival per warp
+        if (lane == 0) peer_entry(a.x.sync);
+        __syncwarp();
     }
-    __syncwarp();
-    const int32_t q0 = __ldg(a.item_ptr + item), q1 = __ldg(a.item_ptr + item + 1);
-    if (q0 >= q1) return;
-    if (a.conj)
-        stream_warp_body<T, true>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0);
-    else
-        stream_warp_body<T, false>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0);
+    if (item < a.nitems) {
+        unsigned char *base = wsm + warp * stream_warp_smem_per_warp<T>();
+        unsigned char *ring = base;
+        const int4 *dring = reinterpret_cast<const int4 *>(base + kWRing);
+        T *xs = reinterpret_cast<T *>(base + kWRing + kWDSlots * kWDBatch * 32);
+        T *ts = xs + kWSegMax;
+        uint64_t *full = reinterpret_cast<uint64_t *>(ts + kWSegMax);
+        uint64_t *dbar = full + kWNB;
+        if (lane == 0) {
+            for (int i = 0; i < kWNB; ++i) mbar_init(&full[i], 33);  // lane 0's expect_tx + 32 cp.async arrivals
+            for (int i = 0; i < kWDSlots; ++i) mbar_init(&dbar[i], 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+        const int32_t q0 = __ldg(a.item_ptr + item), q1 = __ldg(a.item_ptr + item + 1);
+        if (q0 < q1) {
+            if (a.conj)
+                stream_warp_body<T, true>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0);
+            else
+                stream_warp_body<T, false>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0);
+        }
+    }
+    if (a.x.npeer) {
+        __syncwarp();
+        if (lane == 0) peer_exit(a.x.sync);
+    }
 }
 
 // y <- beta*y (beta === false: exact zeros, NaN/Inf in y are not propagated) — first step of the

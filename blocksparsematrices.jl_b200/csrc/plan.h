@@ -172,6 +172,12 @@ struct PeerX {
     const void *peer[8];
     int32_t cuts[9];
     int32_t npeer = 0;
+    // barriers folded into the kernels (kernels.cuh PeerSync): every rank's flag array, this rank's own,
+    // and the three local state words
+    int32_t *const *peer_flags = nullptr;
+    const int32_t *my_flags = nullptr;
+    int32_t *state = nullptr;
+    int32_t rank = 0;
 };
 
 // ---- sparse.cu <-> abi.cu (the handle's internals stay in abi.cu) --------------------------------------

@@ -165,3 +165,23 @@ class SlabMatrix:
                                           c_void_p(y.data_ptr()), self.cuts.ctypes.data_as(POINTER(c_int64)),
                                           c_void_p(st)))
         return y
+
+    def mul_peer_host(self, op, x_host_slab, x_shared, y_dev, y_host_slab, alpha=True, beta=False, stream=None):
+        """The collective multiply with this rank's x / y slabs in HOST memory (NumPy arrays, ideally pinned):
+        bsm_mul_dist_peer_host — H2D of the x slab into x_shared, peer-mode multiply, D2H of the y slab, sync."""
+        import torch
+        D = self.local
+        beta_false = isinstance(beta, (bool, np.bool_)) and not beta
+        a = np.array([alpha], dtype=D.dtype)
+        b = np.array([0 if beta_false else beta], dtype=D.dtype)
+        lo, hi = self.own
+        if x_host_slab.dtype != D.dtype or y_host_slab.dtype != D.dtype or len(x_host_slab) != hi - lo or \
+                len(y_host_slab) != hi - lo:
+            raise ValueError("DimensionMismatch: host slabs must hold this rank's rows in the operator's dtype")
+        st = torch.cuda.current_stream(x_shared.device).cuda_stream if stream is None else stream
+        L.check(L.lib().bsm_mul_dist_peer_host(self.comm._h, D._h, _OPS[op], a.ctypes.data_as(c_void_p),
+                                               b.ctypes.data_as(c_void_p), int(beta_false),
+                                               x_host_slab.ctypes.data_as(c_void_p), c_void_p(x_shared.data_ptr()),
+                                               c_void_p(y_dev.data_ptr()), y_host_slab.ctypes.data_as(c_void_p),
+                                               self.cuts.ctypes.data_as(POINTER(c_int64)), lo, hi, c_void_p(st)))
+        return y_host_slab

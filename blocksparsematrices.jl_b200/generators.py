@@ -97,7 +97,7 @@ def blocksparse_uniform(seed=1, n=10_000, nblocks=2_000, bs=32, dtype=np.float64
 class NearfieldStructure:
     """Structure (no values) of the C2 pattern: leaf boundaries and the near-leaf list of every leaf."""
 
-    def __init__(self, seed, n, leaf_min, leaf_max, k_near):
+    def __init__(self, seed, n, leaf_min, leaf_max, k_near, scattered=False):
         rng = np.random.default_rng(seed)
         self.seed, self.n, self.k_near = seed, n, k_near
         self.bounds = tiling(n, leaf_min, leaf_max, rng)
@@ -105,8 +105,17 @@ class NearfieldStructure:
         self.sizes = np.diff(self.bounds)
         self.near = [np.zeros(0, np.int64)]
         for i in range(1, self.nl):
-            w = np.arange(max(0, i - 2 * k_near), i)
-            self.near.append(np.sort(rng.choice(w, min(len(w), k_near), replace=False)))
+            # banded (default): near leaves among the 2*k_near leaves before i; scattered: anywhere below i, so the
+            # column sets of neighbouring blocks share nothing (no x reuse, no locality for a slab partition)
+            lo = 0 if scattered else max(0, i - 2 * k_near)
+            k = min(i - lo, k_near)
+            if scattered and i > 4 * k_near:
+                pick = np.unique(rng.integers(0, i, 2 * k_near))[:k]
+                while len(pick) < k:
+                    pick = np.unique(np.concatenate([pick, rng.integers(0, i, k_near)]))[:k]
+                self.near.append(np.sort(pick))
+            else:
+                self.near.append(np.sort(rng.choice(np.arange(lo, i), k, replace=False)))
         self.rng = rng
 
     def leaf_cost(self) -> np.ndarray:
@@ -145,17 +154,18 @@ def _fill_block(buf: np.ndarray, seed_key, dtype, symmetric=False):
 
 
 def symmetric_nearfield(seed=2, n=1_000_000, leaf_min=20, leaf_max=200, k_near=6, dtype=np.complex128,
-                        permuted=False, threads=8, leaves=None, return_structure=False):
+                        permuted=False, threads=8, leaves=None, return_structure=False, scattered=False):
     """C2: BEM near-field style SymmetricBlockMatrix. Leaves ~U{leaf_min..leaf_max} tile the n unknowns;
     every leaf has a (symmetrised) diagonal block; every leaf i >= 1 has ONE half-stored off-diagonal
     block whose rows are the leaf and whose columns are the union of min(i, k_near) lower-numbered
     near leaves drawn from the 2*k_near leaves before it (so column sets overlap between blocks, as in
     the reference's cuboid/sphere fixture). With the defaults: ~9.1k leaves, ~12.7 GB of ComplexF64.
-    permuted=True applies a random renumbering of the unknowns (arbitrary index vectors).
+    permuted=True applies a random renumbering of the unknowns (arbitrary index vectors, as the reference's
+    fixture has); scattered=True draws the near leaves from ALL lower-numbered leaves instead of a band.
     Block values come from per-block seeds, so `leaves=(lo, hi)` materialises exactly the blocks the
     slab owning leaves [lo, hi) needs (its diagonal blocks, its off-diagonal rows, and the blocks of
     other leaves whose column set touches the slab) with the same values as in the full matrix."""
-    S = NearfieldStructure(seed, n, leaf_min, leaf_max, k_near)
+    S = NearfieldStructure(seed, n, leaf_min, leaf_max, k_near, scattered=scattered)
     bounds, nl, sizes, near = S.bounds, S.nl, S.sizes, S.near
     perm = (S.rng.permutation(n).astype(np.int64) + 1) if permuted else None
 

@@ -286,15 +286,24 @@ int bsm_dist_allgather_rows(bsm_comm c, int dtype, void *x_dev, int64_t ldx, int
 int bsm_dist_allreduce_max_f64(bsm_comm c, double *dev_values, int64_t count, void *stream);
 /* Peer mode — the all-gather fused into the multiply. bsm_dist_alloc is collective: every rank allocates `bytes`
  * on its GPU and maps every peer's allocation (CUDA IPC, NVLink peer access). Keep a full-length x in such an
- * array; a rank only ever writes its own slab. bsm_mul_dist_peer (nrhs = 1) runs NO collective: after a flag
- * barrier ("every slab of this epoch is written") the multiply kernels fetch each x element from its owner's
- * array over NVLink with the same asynchronous copies that stage it from local HBM (only the entries the rank's
- * blocks touch ever cross the link), and a second flag barrier ("every rank has finished reading") orders
- * whatever follows on the stream — e.g. the solver's update of the slab — after the peers' reads. */
+ * array; a rank only ever writes its own slab. bsm_mul_dist_peer (nrhs = 1) runs NO collective and launches NO
+ * extra kernel: the multiply kernels themselves signal "my x slab of this epoch is written" (first CTA to start),
+ * wait for every peer's signal before their first x fetch, fetch each x element from its owner's array over NVLink
+ * with the same asynchronous copies that stage it from local HBM (only the entries the rank's blocks touch ever
+ * cross the link), and the last CTA to finish signals "done reading" and waits for every peer's — so the kernel
+ * completes only when whatever follows on the stream (the solver's update of the slab) may overwrite x. Every rank
+ * must call it the same number of times, one multiply at a time per communicator. */
 int bsm_dist_alloc(bsm_comm c, size_t bytes, void **dev_ptr);
 int bsm_dist_free(bsm_comm c, void *dev_ptr);   /* only after every rank has finished its last multiply on it */
 int bsm_mul_dist_peer(bsm_comm c, bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
                       void *x_shared, void *y_dev, const int64_t *in_cuts, void *stream);
+/* The same collective multiply with this rank's slabs in HOST memory (what `mul!` on host arrays maps to when the
+ * operator is sharded): H2D of x_host_slab (rows in_cuts[rank] .. in_cuts[rank+1]) into x_shared (and of y_host_slab
+ * when beta is used), bsm_mul_dist_peer, D2H of rows [out_lo, out_hi) of y_dev into y_host_slab, then synchronises
+ * the stream. y_dev is a full-length device work array. */
+int bsm_mul_dist_peer_host(bsm_comm c, bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
+                           const void *x_host_slab, void *x_shared, void *y_dev, void *y_host_slab,
+                           const int64_t *in_cuts, int64_t out_lo, int64_t out_hi, void *stream);
 /* all-gather of x over in_cuts, then bsm_mul on this rank's slab. */
 int bsm_mul_dist(bsm_comm c, bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
                  void *x_dev, int64_t ldx, void *y_dev, int64_t ldy, int64_t nrhs, const int64_t *in_cuts,

@@ -330,27 +330,47 @@ def _scalars(dt, alpha, beta):
     return a, b
 
 
+class CBsm:
+    """Pre-marshalled BlockSparseMatrix for repeated (timed) C-oracle multiplies: block pointers, index pools
+    and the colourings of both index families are built once."""
+
+    def __init__(self, A: OBSM, threads=1):
+        self.A = A
+        self.dt = np.dtype(A.blocks[0].dtype)
+        self.keep, self.bp = _blockptrs(A.blocks, self.dt)
+        self.m = _i64([b.shape[0] for b in A.blocks])
+        self.n = _i64([b.shape[1] for b in A.blocks])
+        self.rpool, self.rptr = _pool(A.rowindices)
+        self.cpool, self.cptr = _pool(A.colindices)
+        self.threads = threads
+        self._colors = {}
+
+    def colors(self, op):
+        key = "N" if op == "N" else "T"
+        if key not in self._colors:
+            if self.threads > 1:
+                self._colors[key] = greedy_colors(self.A.rowindices if op == "N" else self.A.colindices)
+            else:
+                self._colors[key] = _serial_colors(len(self.A.blocks))
+        return self._colors[key]
+
+    def mul(self, x, op="N", alpha=1, beta=0, beta_is_false=True, y=None):
+        A, dt = self.A, self.dt
+        x = np.ascontiguousarray(x, dtype=dt)
+        nout = A.size[0] if op == "N" else A.size[1]
+        y = np.zeros(nout, dt) if y is None else y
+        nc, colptr, colblk = self.colors(op)
+        a, b = _scalars(dt, alpha, beta)
+        rc = c_lib().oracle_bsm_mul(_DT[dt], _OP[op], ctypes.c_int64(len(A.blocks)), self.bp, _p(self.m), _p(self.n),
+                                    _p(self.rpool), _p(self.rptr), _p(self.cpool), _p(self.cptr), ctypes.c_int64(nc),
+                                    _p(colptr), _p(colblk), _p(a), _p(b), int(beta_is_false), _p(x),
+                                    _p(y), ctypes.c_int64(y.size), int(self.threads))
+        assert rc == 0
+        return y
+
+
 def c_mul_bsm(A: OBSM, x, op="N", alpha=1, beta=0, beta_is_false=True, y=None, threads=1):
-    dt = np.dtype(A.blocks[0].dtype)
-    x = np.ascontiguousarray(x, dtype=dt)
-    nout = A.size[0] if op == "N" else A.size[1]
-    y = np.zeros(nout, dt) if y is None else y
-    keep, bp = _blockptrs(A.blocks, dt)
-    m = _i64([b.shape[0] for b in A.blocks])
-    n = _i64([b.shape[1] for b in A.blocks])
-    rpool, rptr = _pool(A.rowindices)
-    cpool, cptr = _pool(A.colindices)
-    if threads > 1:
-        nc, colptr, colblk = greedy_colors(A.rowindices if op == "N" else A.colindices)
-    else:
-        nc, colptr, colblk = _serial_colors(len(A.blocks))
-    a, b = _scalars(dt, alpha, beta)
-    rc = c_lib().oracle_bsm_mul(_DT[dt], _OP[op], ctypes.c_int64(len(A.blocks)), bp, _p(m), _p(n),
-                                _p(rpool), _p(rptr), _p(cpool), _p(cptr), ctypes.c_int64(nc),
-                                _p(colptr), _p(colblk), _p(a), _p(b), int(beta_is_false), _p(x),
-                                _p(y), ctypes.c_int64(y.size), int(threads))
-    assert rc == 0
-    return y
+    return CBsm(A, threads).mul(x, op, alpha, beta, beta_is_false, y)
 
 
 class CSbm:
@@ -395,21 +415,34 @@ def c_mul_sbm(A: OSBM, x, op="N", alpha=1, beta=0, beta_is_false=True, y=None, t
     return CSbm(A, threads).mul(x, op, alpha, beta, beta_is_false, y)
 
 
+class CVbcrs:
+    """Pre-marshalled VBCRS for repeated (timed) C-oracle multiplies."""
+
+    def __init__(self, A: OVBCRS, threads=1):
+        self.A = A
+        self.dt = np.dtype(A.blocks[0].dtype)
+        self.keep, self.bp = _blockptrs(A.blocks, self.dt)
+        self.m = _i64([b.shape[0] for b in A.blocks])
+        self.n = _i64([b.shape[1] for b in A.blocks])
+        self.rowptr, self.cs, self.rs = _i64(A.rowptr), _i64(A.colindices), _i64(A.rowindices)
+        self.threads = threads
+
+    def mul(self, x, op="N", alpha=1, beta=0, beta_is_false=True, y=None):
+        A, dt = self.A, self.dt
+        x = np.ascontiguousarray(x, dtype=dt)
+        nout = A.size[0] if op == "N" else A.size[1]
+        y = np.zeros(nout, dt) if y is None else y
+        a, b = _scalars(dt, alpha, beta)
+        rc = c_lib().oracle_vbcrs_mul(_DT[dt], _OP[op], ctypes.c_int64(len(self.rowptr) - 1), _p(self.rowptr),
+                                      _p(self.cs), _p(self.rs), self.bp, _p(self.m), _p(self.n),
+                                      _p(a), _p(b), int(beta_is_false), _p(x), _p(y),
+                                      ctypes.c_int64(y.size), int(self.threads))
+        assert rc == 0
+        return y
+
+
 def c_mul_vbcrs(A: OVBCRS, x, op="N", alpha=1, beta=0, beta_is_false=True, y=None, threads=1):
-    dt = np.dtype(A.blocks[0].dtype)
-    x = np.ascontiguousarray(x, dtype=dt)
-    nout = A.size[0] if op == "N" else A.size[1]
-    y = np.zeros(nout, dt) if y is None else y
-    keep, bp = _blockptrs(A.blocks, dt)
-    m = _i64([b.shape[0] for b in A.blocks])
-    n = _i64([b.shape[1] for b in A.blocks])
-    a, b = _scalars(dt, alpha, beta)
-    rc = c_lib().oracle_vbcrs_mul(_DT[dt], _OP[op], ctypes.c_int64(len(A.rowptr) - 1), _p(_i64(A.rowptr)),
-                                  _p(_i64(A.colindices)), _p(_i64(A.rowindices)), bp, _p(m), _p(n),
-                                  _p(a), _p(b), int(beta_is_false), _p(x), _p(y),
-                                  ctypes.c_int64(y.size), int(threads))
-    assert rc == 0
-    return y
+    return CVbcrs(A, threads).mul(x, op, alpha, beta, beta_is_false, y)
 
 
 # ----------------------------------------------------------------------------- golden fixture

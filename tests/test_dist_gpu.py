@@ -22,7 +22,22 @@ def _ngpu():
         return 0
 
 
-def _worker(rank, world, port, q):
+def _mixed_bsm(seed, n):
+    """Square BlockSparseMatrix with blocks of 1..300 rows / columns on random contiguous ranges: one multiply runs
+    the CTA-stream, the warp-stream and the gather kernel."""
+    import bsm_b200 as B
+    rng = np.random.default_rng(seed)
+    blocks, rows, cols = [], [], []
+    for _ in range(400):
+        m, k = int(rng.integers(1, 300)), int(rng.integers(1, 300))
+        r0, c0 = int(rng.integers(1, n - m + 2)), int(rng.integers(1, n - k + 2))
+        blocks.append(np.asfortranarray(rng.standard_normal((m, k))))
+        rows.append(np.arange(r0, r0 + m, dtype=np.int64))
+        cols.append(np.arange(c0, c0 + k, dtype=np.int64))
+    return B.BlockSparseMatrix(blocks, rows, cols, (n, n))
+
+
+def _worker(rank, world, port, q, quick=False):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -38,7 +53,13 @@ def _worker(rank, world, port, q):
     errs = {}
     cases = [("sbm", G.symmetric_nearfield(seed=51, n=30000, k_near=4), 1, ("N", "C")),
              ("vbcrs", G.vbcrs_variable(seed=52, n=60000), 1, ("N", "T")),
+             # tall leaves: the CTA-stream kernel AND the gather kernel read x in one multiply (entry barrier in
+             # both, exit barrier in the last one)
+             ("sbm_tall", G.symmetric_nearfield(seed=19, n=20000, leaf_min=150, leaf_max=400, k_near=3), 1, ("N",)),
+             ("bsm_mixed", _mixed_bsm(54, 6000), 1, ("N", "T")),
              ("spmm", G.blocksparse_uniform(seed=53, n=12800, nblocks=3000, bs=32), 16, ("N",))]
+    if quick:
+        cases = cases[:2]
     for name, A, nrhs, ops in cases:
         SM = SlabMatrix(A, comm, ops=ops)
         lo, hi = SM.own
@@ -88,6 +109,37 @@ def _worker(rank, world, port, q):
                 dist.barrier()
                 comm.free(xs)
             assert not np.any(y.cpu().numpy()[:lo] != 0) and not np.any(y.cpu().numpy()[hi:] != 0)
+    if not quick:
+        # a peer-mapped array must survive the NCCL staging buffer growing under it (round-1 defect: the regrow
+        # freed every peer mapping): alloc, peer multiply, a LARGER all-gather, peer multiply again
+        A = G.vbcrs_variable(seed=55, n=40000)
+        SM = SlabMatrix(A, comm, ops=("N",))
+        lo, hi = SM.own
+        n = A.size[0]
+        xt = np.random.default_rng(8).standard_normal(n)
+        ref = oracle_mul(A, xt, "N")[lo:hi]
+        xs = comm.alloc(n, A.dtype)
+        xs.fill_(float("nan"))
+        xs[lo:hi] = torch.from_numpy(xt[lo:hi]).cuda()
+        y3 = torch.zeros_like(xs)
+        SM.mul_peer("N", xs, y3)
+        torch.cuda.synchronize()
+        assert rel2(y3.cpu().numpy()[lo:hi], ref) < 1e-12
+        big = torch.zeros((48, n), dtype=torch.float64, device="cuda").t()      # 48 columns: the stage must grow
+        big[lo:hi] = 1.0
+        comm.allgather_rows(big, SM.cuts)
+        torch.cuda.synchronize()
+        assert bool((big == 1.0).all())
+        y3.zero_()
+        SM.mul_peer("N", xs, y3)
+        torch.cuda.synchronize()
+        errs[("regrow", "N")] = rel2(y3.cpu().numpy()[lo:hi], ref)
+        # host-slab entry point (bsm_mul_dist_peer_host)
+        yh = np.zeros(hi - lo)
+        SM.mul_peer_host("N", np.ascontiguousarray(2 * xt[lo:hi]), xs, y3, yh)
+        errs[("peer_host", "N")] = rel2(yh, 2 * ref)
+        dist.barrier()
+        comm.free(xs)
     out = [None] * world
     dist.all_gather_object(out, errs)
     if rank == 0:
@@ -95,19 +147,30 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
-def test_two_gpu_slabs_match_oracle():
+def run_two_rank_check(quick=False, timeout=600):
+    """Spawns two ranks on GPUs 0 and 1 and returns their error tables (also used by __graft_entry__.smoke())."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, quick)) for r in range(2)]
     for p in procs:
         p.start()
-    out, ver = q.get(timeout=600)
+    try:
+        out, ver = q.get(timeout=timeout)
+    finally:
+        for p in procs:
+            p.join(timeout=120)
+            if p.is_alive():
+                p.kill()
     for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+        assert p.exitcode == 0, f"rank exited with {p.exitcode}"
     assert ver >= 21800
     for errs in out:
         assert all(e < 1e-12 for e in errs.values()), errs
+    return out
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs two GPUs")
+def test_two_gpu_slabs_match_oracle():
+    run_two_rank_check(quick=False)
