@@ -32,7 +32,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 from pathlib import Path
 
@@ -148,49 +147,69 @@ def host_x(n, nrhs, dtype, seed=1234):
 
 
 # ----------------------------------------------------------------------------- clocks
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as N
+N.nvmlInit()
+h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+print("max", N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM), flush=True)
+while True:
+    try:
+        print(time.time(), N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), reasons(h), flush=True)
+    except Exception:
+        pass
+    time.sleep(0.0005)
+"""
+
+
 class ClockSampler:
-    """NVML polled back to back from a thread while the timed region runs (the region lasts tens of ms: sleeping
-    between polls would leave a single sample)."""
+    """NVML polled every ~0.5 ms by a SEPARATE process (a thread in this process competes with the launch loop for the
+    GIL and stalls it); only the samples stamped inside the timed region are kept."""
 
     def __init__(self, index=0):
-        self.index, self.samples, self.nvml, self._stop = index, [], None, True
+        self.index, self.proc, self.t0, self.t1 = index, None, None, None
 
-    def _poll(self):
-        N = self.nvml
-        h = N.nvmlDeviceGetHandleByIndex(self.index)
-        reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
-        while not self._stop:
-            try:
-                self.samples.append((N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), reasons(h)))
-            except Exception:
-                time.sleep(0.001)
+    def launch(self):
+        import subprocess
+        try:
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.first = self.proc.stdout.readline()      # "max <MHz>": the sampler is up
+        except Exception:
+            self.proc = None
 
     def start(self):
-        try:
-            import pynvml as N
-            N.nvmlInit()
-            self.nvml = N
-            self.sm_max = N.nvmlDeviceGetMaxClockInfo(N.nvmlDeviceGetHandleByIndex(self.index), N.NVML_CLOCK_SM)
-            self._stop = False
-            self.thread = threading.Thread(target=self._poll, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.nvml = None
+        self.t0 = time.time()
 
     def stop(self):
-        if self.nvml is None:
+        self.t1 = time.time()
+        if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
-        N = self.nvml
-        self._stop = True
-        self.thread.join(timeout=1.0)
-        names = {"hw_slowdown": getattr(N, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-                 "hw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-                 "sw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-                 "sw_power_cap": getattr(N, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-        sm = [a for a, _ in self.samples]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.sm_max),
-                "reasons": sorted(k for k, bit in names.items() if any(r & bit for _, r in self.samples)),
-                "samples": len(sm), "source": "nvml polled back to back during the timed region"}
+        time.sleep(0.01)
+        self.proc.terminate()
+        out = self.proc.stdout.read().splitlines()
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        sm, rs, all_sm = [], 0, []
+        for ln in out:
+            f = ln.split()
+            if len(f) != 3:
+                continue
+            try:
+                ts, clk, r = float(f[0]), float(f[1]), int(f[2])
+            except ValueError:
+                continue
+            all_sm.append(clk)
+            if self.t0 <= ts <= self.t1:
+                sm.append(clk)
+                rs |= r
+        try:
+            mx = float(self.first.split()[1])
+        except Exception:
+            mx = None
+        return {"sm_mhz": float(np.median(sm)) if sm else (float(np.median(all_sm)) if all_sm else None), "sm_max_mhz": mx,
+                "reasons": sorted(k for k, b in bits.items() if rs & b), "samples": len(sm),
+                "source": "nvml polled every ~0.5 ms by a separate process; samples stamped inside the timed region"}
 
 
 # ----------------------------------------------------------------------------- CPU arm (oracle)
@@ -347,6 +366,8 @@ def run_workload(cx, name, primary):
         step()
     barrier()
     sampler = ClockSampler(local)
+    if rank == 0 and primary:
+        sampler.launch()
     l2_resident = work["bytes"] <= 4 * 126e6
     inline_prof = not l2_resident
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "plan.h"
 #include "spmm.cuh"
+#include "spmm_tma.cuh"
 
 using namespace bsm;
 
@@ -104,6 +105,10 @@ struct bsm_matrix {
     // sparse(A) result built by bsm_sparse_build (sparse.cu), device arrays
     void *sparse_slot[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool restricted = false;
+    // tensor maps of the arena for spmm_tma_kernel (encoded on the first multi-RHS multiply)
+    TmaMaps tma_maps;
+    bool tma_maps_ready = false;
+    std::mutex tma_mu;
     // partial-sum scratch: one persistent buffer per launch stream (sized for the largest plan), so that a multiply
     // allocates nothing and concurrent multiplies on different streams never share partial sums
     std::mutex scratch_mu;
@@ -434,6 +439,129 @@ int ensure_attrs(int device) {
     return 0;
 }
 
+// ---- spmm_tma_kernel: tensor maps and launch -------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+int encode_2d(CUtensorMap *map, CUtensorMapDataType dt, void *base, uint64_t d0, uint64_t d1, uint64_t stride1_bytes,
+              uint32_t b0, uint32_t b1) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail(BSM_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
+    const cuuint64_t dims[2] = {d0, d1};
+    const cuuint64_t strides[1] = {stride1_bytes};
+    const cuuint32_t box[2] = {b0, b1};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(BSM_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return 0;
+}
+
+template <class T>
+int ensure_arena_maps(bsm_matrix *A) {
+    std::lock_guard<std::mutex> lk(A->tma_mu);
+    if (A->tma_maps_ready) return 0;
+    const uint64_t rows = (uint64_t)A->H.arena_elems * sizeof(T) / 128;
+    for (int q = 0; q < 4; ++q)   // the arena as rows of 128 bytes; box q covers ARows >> q rows
+        if (int rc = encode_2d(&A->tma_maps.a[q], CU_TENSOR_MAP_DATA_TYPE_UINT8, A->arena, 128, rows, 128, 128,
+                               (uint32_t)(TmaGeom<T>::ARows >> q)))
+            return rc;
+    A->tma_maps_ready = true;
+    return 0;
+}
+
+template <class T, int NB>
+int launch_spmm_tma_nb(bsm_matrix *A, const HostPlan &HP, const DevPlan &DP, const TmaSpmmArgs<T> &args, const T *x, int64_t ldx,
+                       int64_t nin, int64_t nrhs, cudaStream_t st) {
+    static std::mutex mu;
+    static bool attr_done[64] = {};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!attr_done[A->device & 63]) {
+            CUDA_TRY(cudaFuncSetAttribute(spmm_tma_kernel<T, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)spmm_tma_smem_bytes<T, NB>()));
+            attr_done[A->device & 63] = true;
+        }
+    }
+    TmaMaps maps = A->tma_maps;
+    constexpr bool is_c = sizeof(T) == 16;
+    constexpr bool is_f = sizeof(T) == 4;
+    // X as (contraction entries) x (right-hand sides); ComplexF64 is described as interleaved doubles
+    if (int rc = encode_2d(&maps.x, is_f ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (void *)x,
+                           (uint64_t)nin * (is_c ? 2 : 1), (uint64_t)nrhs, (uint64_t)ldx * sizeof(T), is_f ? 32 : 16, NB))
+        return rc;
+    TmaSpmmArgs<T> a = args;
+    a.nstages = spmm_tma_stages<T, NB>();
+    dim3 grid((unsigned)(HP.mitem_ptr.size() - 1), (unsigned)((nrhs + NB - 1) / NB));
+    spmm_tma_kernel<T, NB><<<grid, kTThreads, spmm_tma_smem_bytes<T, NB>(), st>>>(a, maps);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Multi-RHS multiply through spmm_tma_kernel. Returns 1 when the call is not eligible (the caller falls back).
+template <class T>
+int launch_spmm_tma(bsm_matrix *A, int op, const HostPlan &HP, const DevPlan &DP, const void *alpha, const void *beta,
+                    int beta_is_false, const T *x, int64_t ldx, T *y, int64_t ldy, int64_t nrhs, cudaStream_t st) {
+    if (!HP.spmm_tma || !encode_tiled_fn()) return 1;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || ((uint64_t)ldx * sizeof(T)) % 16 != 0) return 1;   // TMA alignment rules
+    if (int rc = ensure_arena_maps<T>(A)) return rc;
+    TmaSpmmArgs<T> a;
+    a.contrib = DP.contrib.p;
+    a.slices = DP.mslices.p;
+    a.item_ptr = DP.mitem_ptr.p;
+    a.set_start = A->set_start.p;
+    a.set_pool_off = A->set_pool_off.p;
+    a.pool = A->pool.p;
+    a.y = y;
+    a.ldy = ldy;
+    std::memcpy(&a.alpha, alpha, sizeof(T));
+    std::memset(&a.beta, 0, sizeof(T));
+    if (!beta_is_false) std::memcpy(&a.beta, beta, sizeof(T));
+    a.nrhs = (int32_t)nrhs;
+    a.beta_false = beta_is_false ? 1 : 0;
+    a.conj = (op == BSM_OP_C && sizeof(T) == 16) ? 1 : 0;
+    a.nstages = 0;
+    a.elem_shift = sizeof(T) == 4 ? 2 : sizeof(T) == 8 ? 3 : 4;
+    const int64_t nin = HP.in_dim;
+    const bool prof = A->profiling;
+    if (prof) CUDA_TRY(cudaEventRecord(A->ev[0], st));
+    int rc;
+    constexpr int kMaxNB = sizeof(T) == 16 ? 32 : 64;
+    const int64_t want = std::min<int64_t>(nrhs, kMaxNB);
+    if (want <= 8)
+        rc = launch_spmm_tma_nb<T, 8>(A, HP, DP, a, x, ldx, nin, nrhs, st);
+    else if (want <= 16)
+        rc = launch_spmm_tma_nb<T, 16>(A, HP, DP, a, x, ldx, nin, nrhs, st);
+    else if (want <= 32 || kMaxNB == 32)
+        rc = launch_spmm_tma_nb<T, 32>(A, HP, DP, a, x, ldx, nin, nrhs, st);
+    else
+        rc = launch_spmm_tma_nb<T, (sizeof(T) == 16 ? 32 : 64)>(A, HP, DP, a, x, ldx, nin, nrhs, st);
+    if (rc) return rc;
+    if (prof) CUDA_TRY(cudaEventRecord(A->ev[1], st));
+    const int64_t nu = (int64_t)HP.muncovered.size();
+    if (nu > 0) {   // rows no block touches: y = beta*y
+        for (int64_t jb = 0; jb < nrhs; jb += 65535) {   // grid.y limit
+            dim3 fg((unsigned)((nu + 255) / 256), (unsigned)std::min<int64_t>(65535, nrhs - jb));
+            spmm_uncovered_kernel_t<T><<<fg, 256, 0, st>>>(DP.muncovered.p, nu, y + jb * ldy, ldy, a.beta, a.beta_false);
+        }
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (prof) CUDA_TRY(cudaEventRecord(A->ev[2], st));
+    return 0;
+}
+
 // phase 0: the whole multiply. Slab handles under bsm_mul_dist (nrhs = 1, scratch owned by the caller and passed
 // through *scratch_io): phase 1 = the slices whose inputs are rank-local (run while x is being all-gathered),
 // phase 2 = the remote slices (on a second stream, so the two grids fill each other's tails), phase 3 = the
@@ -528,8 +656,14 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
         }
         return 0;
     }
+    // many right-hand sides: one pass over A on the FP64 tensor cores instead of nrhs SpMV passes. Regular plans (blocks
+    // of <= 32 rows, contiguous input sets) of every dtype: spmm_tma_kernel; other Float64 plans: spmm_dmma_kernel
+    if (nrhs >= kSpmmMinRhs && HP.spmm_ok && HP.spmm_tma && A->variant != BSM_VARIANT_GATHER && p >= 2 && p < 4 && phase == 0 &&
+        !(px && px->npeer > 0) && A->variant != BSM_VARIANT_FUSED) {   // FUSED: comparison, round-1 SpMM kernel
+        const int rc = launch_spmm_tma<T>(A, op, HP, DP, alpha, beta, beta_is_false, x, ldx, y, ldy, nrhs, st);
+        if (rc <= 0) return rc;
+    }
     if constexpr (sizeof(T) == 8) {
-        // many right-hand sides: one pass over A on the FP64 tensor cores instead of nrhs SpMV passes
         if (nrhs >= kSpmmMinRhs && HP.spmm_ok && A->variant != BSM_VARIANT_GATHER && p >= 2) {
             SpmmArgs m;
             m.arena = (const double *)A->arena;
@@ -594,6 +728,7 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             a.x.sync.rank = px->rank;
             a.x.sync.do_exit = 0;
             a.x.sync.arrivals = 1;
+            a.x.sync.debug = px->debug;
             if (last_kind < 0) {   // nothing to multiply on this rank: the barriers alone
                 PeerSync ps = a.x.sync;
                 ps.do_exit = 1;
@@ -1206,6 +1341,7 @@ int bsm_plan_stats(bsm_handle h, int op, int64_t out[12]) {
     out[8] = P.scratch_elems;
     out[9] = (int64_t)P.gather_rows.size();
     out[10] = P.spmm_ok ? (int64_t)P.mitem_ptr.size() - 1 : 0;
+    out[11] = (P.spmm_ok && P.spmm_tma) ? 1 : 0;
     return 0;
 }
 

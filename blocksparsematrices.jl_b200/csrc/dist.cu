@@ -104,6 +104,7 @@ struct bsm_comm_s {
     int32_t *flags = nullptr;               // this rank's flag array: ready[nranks], done[nranks]
     int32_t **peer_flags_dev = nullptr;     // device array: every rank's flag array
     int32_t *sync_state = nullptr;          // local device words of the in-kernel barriers (kernels.cuh PeerSync)
+    int debug = 0;                          // benchmarking only: bit0 no entry wait, bit1 no exit wait
 };
 
 namespace {
@@ -276,6 +277,12 @@ int bsm_dist_allgather_rows(bsm_comm c, int dtype, void *x_dev, int64_t ldx, int
     return 0;
 }
 
+int bsm_dist_set_debug(bsm_comm c, int flags) {
+    if (!c) return dfail(BSM_ERR_ARG, "null communicator");
+    c->debug = flags;
+    return 0;
+}
+
 int bsm_dist_set_collective(bsm_comm c, int use_broadcasts) {
     if (!c) return dfail(BSM_ERR_ARG, "null communicator");
     c->use_broadcasts = use_broadcasts ? 1 : 0;
@@ -392,6 +399,7 @@ int bsm_mul_dist_peer(bsm_comm c, bsm_handle h, int op, const void *alpha, const
     px.my_flags = c->flags;
     px.state = c->sync_state;
     px.rank = c->rank;
+    px.debug = c->debug;
     void *scratch = nullptr;
     return bsm_mul_phase(h, op, alpha, beta, beta_is_false, x_shared, y_dev, stream, 0, &scratch, &px);
 }

@@ -101,8 +101,8 @@ constexpr int kMaxPeers = 8;
 
 // Peer-mode barriers folded into the multiply kernels (no extra launches). Every rank owns a flag array in
 // peer-mapped memory: ready[nranks] then done[nranks], written by the peers with the epoch (= index of the
-// multiply) they have reached. `state` are three words in LOCAL device memory: [0] epochs completed,
-// [1] epoch whose "ready" signal has been sent, [2] arrival counter of the exit barrier.
+// multiply) they have reached. `state` are four words in LOCAL device memory: [0] epochs completed, [1] epoch whose
+// "ready" signal has been sent, [2] arrival counter of the exit barrier, [3] epoch whose entry barrier has been passed.
 //   entry  (every kernel of the multiply that reads x; one thread per CTA / warp, before the first x read):
 //          the first arrival tells every peer "my x slab of this epoch is written" (the kernel runs after the
 //          stream work that wrote it), then everybody waits until every peer has said so;
@@ -117,35 +117,58 @@ struct PeerSync {
     int32_t nranks, rank;
     int32_t do_exit;      // this kernel runs the exit barrier
     int32_t arrivals;     // arrivals the exit barrier expects
+    int32_t debug;        // benchmarking only (bsm_dist_set_debug): bit0 skip the entry wait, bit1 skip the exit wait,
+                          // bit2 every arrival does the system-scope wait itself
 };
 
+__device__ __forceinline__ int32_t ld_acquire_sys(const int32_t *p) {
+    int32_t v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int32_t *p, int32_t v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// waits until *flag >= epoch (acquire: what the writer published before its release store is visible afterwards)
 __device__ __forceinline__ void peer_spin(const int32_t *flag, int32_t epoch) {
-    const volatile int32_t *f = flag;
-    if (*f >= epoch) return;
+    if (ld_acquire_sys(flag) >= epoch) return;
     const long long t0 = clock64();
-    while (*f < epoch) {
+    while (ld_acquire_sys(flag) < epoch) {
         __nanosleep(64);
         if (clock64() - t0 > 120000000000ll) __trap();   // ~60 s: a peer died or never entered the collective call
     }
 }
+__device__ __forceinline__ int32_t ld_acquire_gpu(const int32_t *p) {
+    int32_t v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int32_t *p, int32_t v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Thousands of CTAs / warps pass here; a system-scope acquire by each of them costs ~50 us per multiply (measured on
+// C3, 2 GPUs). So the system-scope wait on the peers' flags is done by whoever arrives while state[3] ("entry passed")
+// is still behind; it then publishes the epoch in state[3] with a device-scope release, and everybody else gets by
+// with ONE device-scope acquire of that local word (the synchronisation chain peer -> first arrival -> this thread
+// is transitive).
 __device__ __forceinline__ void peer_entry(const PeerSync &s) {
     const int32_t e = *reinterpret_cast<volatile int32_t *>(s.state) + 1;
-    if (atomicMax(s.state + 1, e) < e) {
-        __threadfence_system();
-        for (int p = 0; p < s.nranks; ++p) *reinterpret_cast<volatile int32_t *>(s.peer_flags[p] + s.rank) = e;
+    if (*reinterpret_cast<volatile int32_t *>(s.state + 1) < e && atomicMax(s.state + 1, e) < e) {
+        for (int p = 0; p < s.nranks; ++p) st_release_sys(s.peer_flags[p] + s.rank, e);
     }
+    if (s.debug & 1) return;
+    if (!(s.debug & 4) && ld_acquire_gpu(s.state + 3) >= e) return;
     for (int p = 0; p < s.nranks; ++p) peer_spin(s.my_flags + p, e);
-    __threadfence_system();
+    if (!(s.debug & 4)) st_release_gpu(s.state + 3, e);
 }
 __device__ __forceinline__ void peer_exit(const PeerSync &s) {
     if (!s.do_exit) return;
     __threadfence();
     if (atomicAdd(s.state + 2, 1) != s.arrivals - 1) return;
     const int32_t e = *reinterpret_cast<volatile int32_t *>(s.state) + 1;
-    __threadfence_system();
-    for (int p = 0; p < s.nranks; ++p)
-        *reinterpret_cast<volatile int32_t *>(s.peer_flags[p] + s.nranks + s.rank) = e;
-    for (int p = 0; p < s.nranks; ++p) peer_spin(s.my_flags + s.nranks + p, e);
+    for (int p = 0; p < s.nranks; ++p) st_release_sys(s.peer_flags[p] + s.nranks + s.rank, e);
+    if (!(s.debug & 2))
+        for (int p = 0; p < s.nranks; ++p) peer_spin(s.my_flags + s.nranks + p, e);
     *reinterpret_cast<volatile int32_t *>(s.state + 2) = 0;
     *reinterpret_cast<volatile int32_t *>(s.state) = e;
     __threadfence();

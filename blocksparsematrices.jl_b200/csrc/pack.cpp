@@ -602,6 +602,13 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
             total += (int64_t)c.m * c.n * s;
             if (c.m > 32 || ((c.form & kFormT) && c.n > 32)) P.spmm_small = false;
         }
+        P.spmm_tma = true;
+        for (const auto &c : P.contrib) {
+            if (c.m == 0 || c.n == 0) continue;
+            if (c.m > 32 || ((c.form & kFormT) && c.n > 32) || S.start[c.in_set] < 0) P.spmm_tma = false;
+        }
+        for (size_t g = 0; g < G; ++g)
+            if (S.len[gset[g]] > 32) P.spmm_tma = false;
         for (size_t g = 0; g < G; ++g) {
             if (S.len[gset[g]] == 0) continue;
             bsm_slice sl;

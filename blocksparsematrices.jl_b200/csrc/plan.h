@@ -117,6 +117,8 @@ struct HostPlan {
     std::vector<bsm_slice> mslices;     // SpMM: one (direct, whole-segment) slice per block row, never split
     std::vector<int32_t> muncovered;    // SpMM: owned rows no block touches (y <- beta*y there)
     bool spmm_small = false;            // no block has more than 32 rows or columns (4-stage ring)
+    bool spmm_tma = false;              // eligible for spmm_tma_kernel: segments and blocks of <= 32 rows, T-form blocks of
+                                        // <= 32 columns, every input index set a contiguous range (X tiles are TMA boxes)
     std::vector<int32_t> mitem_ptr;
     std::vector<int32_t> gather_rows;
     std::vector<int64_t> gather_ptr;
@@ -178,6 +180,7 @@ struct PeerX {
     const int32_t *my_flags = nullptr;
     int32_t *state = nullptr;
     int32_t rank = 0;
+    int32_t debug = 0;
 };
 
 // ---- sparse.cu <-> abi.cu (the handle's internals stay in abi.cu) --------------------------------------

@@ -195,7 +195,8 @@ class DeviceMatrix:
         names = ("sym_fused_tma_kernel", "stream_warp_kernel", "gather_gemv_kernel")
         return {"slices": dict(zip(names, out[0:3].tolist())), "bytes": dict(zip(names, out[3:6].tolist())),
                 "warp_items": int(out[6]), "warp_chunks": int(out[7]), "scratch_elems": int(out[8]),
-                "finalized_rows": int(out[9]), "spmm": int(out[10])}
+                "finalized_rows": int(out[9]), "spmm": int(out[10]),
+                "spmm_kernel": "spmm_tma_kernel" if out[11] else "spmm_dmma_kernel"}
 
     def set_profiling(self, on: bool):
         L.check(L.lib().bsm_set_profiling(self._h, int(on)))
@@ -251,9 +252,12 @@ class DeviceMatrix:
             if x.shape[0] != nin:
                 raise ValueError(f"DimensionMismatch: x has {x.shape[0]} rows, operator needs {nin}")
             nrhs = 1 if x.dim() == 1 else x.shape[1]
-            xm = x if x.dim() == 1 else x.t().contiguous().t()      # column-major storage
-            if x.dim() == 1 and not x.is_contiguous():
-                xm = x.contiguous()
+            if x.dim() == 1:
+                xm = x if x.is_contiguous() else x.contiguous()
+            elif x.stride(0) == 1 and x.stride(1) >= nin:
+                xm = x                                               # column-major already (any leading dimension)
+            else:
+                xm = x.t().contiguous().t()                          # column-major storage
             if y is None:
                 if not beta_false:
                     raise ValueError("beta needs an existing y")

@@ -45,6 +45,9 @@ class Comm:
     def set_collective(self, use_broadcasts: bool):
         L.check(L.lib().bsm_dist_set_collective(self._h, int(use_broadcasts)))
 
+    def set_debug(self, flags: int):
+        L.check(L.lib().bsm_dist_set_debug(self._h, int(flags)))
+
     def nccl_version(self) -> int:
         v = c_int(0)
         L.check(L.lib().bsm_dist_info(self._h, None, None, byref(v)))

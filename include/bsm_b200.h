@@ -163,8 +163,9 @@ int bsm_launch_count(bsm_handle h, int op);
  * the CTA-stream kernel (sym_fused_tma_kernel), the warp-stream kernel (stream_warp_kernel) and the
  * gather kernel (gather_gemv_kernel); out[3..5] = block bytes each of them streams; out[6] = warp work
  * items; out[7] = warp-stream chunks; out[8] = scratch elements; out[9] = rows finalised by the gather pass;
- * out[10] = CTA work items of the multi-RHS (SpMM) kernel, 0 if the plan is not eligible for it (then
- * nrhs > 1 loops over the columns); out[11] reserved. */
+ * out[10] = CTA work items of the multi-RHS (SpMM) kernels, 0 if the plan is not eligible for them (then
+ * nrhs > 1 loops over the columns); out[11] = 1 if the plan is eligible for spmm_tma_kernel (every dtype), else
+ * multi-RHS products use spmm_dmma_kernel (Float64 only). */
 int bsm_plan_stats(bsm_handle h, int op, int64_t out[12]);
 
 /* ---- table export (bit-exact packing checks) ---------------------------------------------- */
@@ -278,6 +279,9 @@ int bsm_dist_set_overlap(bsm_comm c, int on);
 /* 0 (default): equal-chunk staging + one ncclAllGather; 1: one NCCL group of in-place broadcasts per rank and
  * right-hand side (no staging; 10x slower on 8 GPUs, kept for comparison). */
 int bsm_dist_set_collective(bsm_comm c, int use_broadcasts);
+/* Benchmarking only: bit0 = peer-mode multiplies skip the wait of the entry barrier, bit1 = of the exit barrier
+ * (results are then only valid when x does not change between multiplies). */
+int bsm_dist_set_debug(bsm_comm c, int flags);
 int bsm_dist_info(bsm_comm c, int *nranks, int *rank, int *nccl_version);
 /* In-place all-gather of the row slabs of a column-major (rows x nrhs, leading dimension ldx) DEVICE
  * array: on return every rank holds all rows. cuts has nranks+1 entries (0-based, non-decreasing). */

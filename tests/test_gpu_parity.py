@@ -245,43 +245,86 @@ def test_real_matrix_complex_x_promotes():
     assert rel2(y, ref) < 1e-12
 
 
-# ---- multi-RHS SpMM (C5): FP64 tensor-core kernel vs the oracle applied column by column ------------------
-def spmm_check(A, nrhs, ops=OPS, seed=3):
+# ---- multi-RHS SpMM (C5): tensor-core kernels vs the oracle applied column by column ----------------------
+def spmm_check(A, nrhs, ops=OPS, seed=3, expect_kernel=None):
+    """Matrix right-hand sides of every dtype: spmm_tma_kernel (regular plans) / spmm_dmma_kernel (other Float64
+    plans) / the column loop must all reproduce the oracle applied column by column (what LinearMaps does)."""
     import torch
     rng = np.random.default_rng(seed)
     D = A.device()
+    dt = np.dtype(A.dtype)
+    tol = TOL[dt]
+    f64 = dt == np.float32
+    tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
+           np.dtype(np.complex128): torch.complex128}[dt]
+    alpha, beta = (0.7 + 0.3j, -0.4 + 0.2j) if dt.kind == "c" else (0.7, -0.4)
+
+    def rnd(shape):
+        v = rng.standard_normal(shape)
+        if dt.kind == "c":
+            v = v + 1j * rng.standard_normal(shape)
+        return np.asfortranarray(v.astype(dt))
+
     for op in ops:
-        assert D.plan_stats(op)["spmm"], "plan is not eligible for the SpMM kernel"
+        st = D.plan_stats(op)
+        assert st["spmm"], "plan is not eligible for the SpMM kernels"
+        if expect_kernel:
+            assert st["spmm_kernel"] == expect_kernel, st
         nin = A.size[1] if op == "N" else A.size[0]
         nout = A.size[0] if op == "N" else A.size[1]
-        X = np.asfortranarray(rng.standard_normal((nin, nrhs)))
-        Y0 = np.asfortranarray(rng.standard_normal((nout, nrhs)))
-        ref = np.stack([oracle_mul(A, np.ascontiguousarray(X[:, j]), op) for j in range(nrhs)], axis=1)
+        X, Y0 = rnd((nin, nrhs)), rnd((nout, nrhs))
+        ref = np.stack([oracle_mul(A, np.ascontiguousarray(X[:, j]), op, f64=f64) for j in range(nrhs)], axis=1)
         Y = wrap(A, op) * X                                        # host pointers (bsm_mul_host)
-        assert Y.shape == (nout, nrhs) and rel2(Y, ref) < 1e-12, (op, nrhs)
-        ref5 = np.stack([oracle_mul(A, np.ascontiguousarray(X[:, j]), op, 0.7, -0.4, False, Y0[:, j].copy())
+        assert Y.shape == (nout, nrhs) and Y.dtype == dt and rel2(Y, ref) < tol, (op, nrhs, rel2(Y, ref))
+        ref5 = np.stack([oracle_mul(A, np.ascontiguousarray(X[:, j]), op, alpha, beta, False, Y0[:, j].copy(), f64=f64)
                          for j in range(nrhs)], axis=1)
-        Y5 = B.mul_(Y0.copy(order="F"), wrap(A, op), X, 0.7, -0.4)
-        assert rel2(Y5, ref5) < 1e-12, (op, nrhs, "5-arg")
-        # device pointers with a padded leading dimension
-        Xd = torch.zeros((nrhs, nin + 3), dtype=torch.float64, device="cuda").t()[:nin]
-        Xd.copy_(torch.from_numpy(X))
-        Yd = D.mul(op, Xd)
-        assert rel2(Yd.cpu().numpy(), ref) < 1e-12
-        # the column loop over the SpMV kernels (what LinearMaps does) gives the same answer
-        D.set_variant(L.VARIANT_GATHER)
-        assert rel2(D.mul(op, X), ref) < 1e-12
+        Y5 = B.mul_(Y0.copy(order="F"), wrap(A, op), X, alpha, beta)
+        assert rel2(Y5, ref5) < tol, (op, nrhs, "5-arg", rel2(Y5, ref5))
+        # device pointers with a padded leading dimension: even padding keeps the TMA path, odd padding breaks the
+        # 16-byte stride rule of the tensor map and must fall back without changing the answer
+        for pad in (4, 3):
+            Xd = torch.zeros((nrhs, nin + pad), dtype=tdt, device="cuda").t()[:nin]
+            Xd.copy_(torch.from_numpy(X))
+            Yd = D.mul(op, Xd)
+            assert rel2(Yd.cpu().numpy(), ref) < tol, (op, nrhs, "pad", pad)
+        # the round-1 kernel (Float64) / the column loop over the SpMV kernels give the same answer
+        for variant in (L.VARIANT_FUSED, L.VARIANT_GATHER):
+            D.set_variant(variant)
+            assert rel2(D.mul(op, X), ref) < tol, (op, nrhs, "variant", variant)
         D.set_variant(L.VARIANT_AUTO)
 
 
 @pytest.mark.parametrize("nrhs", [8, 13, 64, 70])
-def test_c5_shape_spmm(nrhs):
-    A = G.blocksparse_uniform(seed=31, n=6400, nblocks=1500, bs=32)
-    spmm_check(A, nrhs)
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32])
+def test_c5_shape_spmm(nrhs, dtype):
+    A = G.blocksparse_uniform(seed=31, n=6400, nblocks=1500, bs=32, dtype=dtype)
+    spmm_check(A, nrhs, expect_kernel="spmm_tma_kernel")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32])
+def test_spmm_small_variable_blocks(dtype):
+    # blocks of 8..32 rows / columns: masked (partial-slab) stages, segments shorter than 32 rows, wide blocks cut
+    # into 32-wide contraction slabs
+    spmm_check(G.vbcrs_variable(seed=36, n=12000, tile_min=8, tile_max=32, dtype=dtype), 24, expect_kernel="spmm_tma_kernel")
+    spmm_check(G.vbcrs_variable(seed=37, n=4000, tile_min=1, tile_max=19, dtype=dtype), 9, expect_kernel="spmm_tma_kernel")
+
+
+def test_spmm_wide_blocks_of_short_rows():
+    # N-form blocks far wider than one contraction slab (32 x 100), T-form falls back (columns > 32)
+    rng = np.random.default_rng(38)
+    n = 3200
+    blocks, rows, cols = [], [], []
+    for r in range(0, n, 32):
+        c0 = int(rng.integers(0, n - 100))
+        blocks.append(np.asfortranarray(rng.standard_normal((32, 100))))
+        rows.append(np.arange(r + 1, r + 33, dtype=np.int64))
+        cols.append(np.arange(c0 + 1, c0 + 101, dtype=np.int64))
+    A = B.BlockSparseMatrix(blocks, rows, cols, (n, n))
+    spmm_check(A, 16, ops=("N",), expect_kernel="spmm_tma_kernel")
 
 
 def test_spmm_variable_blocks_and_permuted_indices():
-    spmm_check(G.vbcrs_variable(seed=32, n=20000), 24)                       # odd sizes: 8-byte copy paths
+    spmm_check(G.vbcrs_variable(seed=32, n=20000), 24)                       # blocks up to 64 rows: round-1 kernel
     spmm_check(G.blocksparse_uniform(seed=33, n=3200, nblocks=400, bs=32, permuted=True), 16)   # index pool
     spmm_check(G.blocksparse_uniform(seed=34, n=2560, nblocks=300, bs=64), 32)                 # 64-row blocks
 
