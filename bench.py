@@ -335,7 +335,7 @@ def run_workload(cx, name, primary):
         D, own = SM.local, SM.own
         work = c2_whole_job_work(spec, "scattered" in hard) if rb is not None else host_work(A, op, nrhs)
     else:
-        D = B.DeviceMatrix(A, device=local, variant=args.variant)
+        D = B.DeviceMatrix(A, device=local, variant=args.variant, plan_hints=args.plan_hints)
         own = (0, nout)
         work = host_work(A, op, nrhs)
     torch.cuda.synchronize()
@@ -517,7 +517,7 @@ def run_workload(cx, name, primary):
         kernel_name = "sym_fused_kernel"
     tensor = None
     if nrhs >= 8 and stats["spmm"] and args.variant != 1:
-        kernel_name = stats.get("spmm_kernel", "spmm_dmma_kernel")
+        kernel_name = "spmm_dmma_kernel" if args.variant == 2 else stats.get("spmm_kernel", "spmm_dmma_kernel")
         dgemm_tf = dgemm_peak(torch, dev)
         ach_tf = local_work["flops"] / (k_ms * 1e-3) / 1e12
         tensor = {"bound": "tensor", "achieved": ach_tf, "peak": dgemm_tf, "unit": "TFLOP/s", "frac": ach_tf / dgemm_tf,
@@ -594,6 +594,7 @@ def main():
     ap.add_argument("--broadcasts", action="store_true", help="N > 1: grouped in-place broadcasts instead of the all-gather")
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-gather, then multiply, on one stream")
     ap.add_argument("--op", default=None, choices=["N", "T", "C"], help="override the workload's op (development)")
+    ap.add_argument("--plan-hints", type=int, default=0, help="bsm_options.plan_hints (development)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="default workload only: skip the c3 / c5 companion results")
     args = ap.parse_args()

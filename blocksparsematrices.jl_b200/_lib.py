@@ -25,7 +25,11 @@ class Options(ctypes.Structure):
     _fields_ = [("device", c_int32), ("variant", c_int32),
                 ("own_row_lo", c_int64), ("own_row_hi", c_int64),
                 ("own_col_lo", c_int64), ("own_col_hi", c_int64),
-                ("reserved", c_int64 * 4)]
+                ("plan_hints", c_int64), ("reserved", c_int64 * 3)]
+
+
+class CgOptions(ctypes.Structure):
+    _fields_ = [("rtol", c_double), ("maxit", c_int64), ("hermitian", c_int32), ("check_every", c_int32)]
 
 
 class BsmError(RuntimeError):
@@ -86,6 +90,11 @@ SIGNATURES = [
                                        c_void_p, _P64, c_int64, c_int64, c_void_p]),
     ("bsm_mul_dist", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p,
                              c_int64, c_int64, _P64, c_void_p]),
+    ("bsm_dist_allreduce_sum_f64", c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    ("bsm_cg_default_options", None, [POINTER(CgOptions)]),
+    ("bsm_cg", c_int, [c_void_p, c_void_p, c_void_p, POINTER(CgOptions), _P64, POINTER(c_double), c_void_p]),
+    ("bsm_cg_dist", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, _P64, POINTER(CgOptions), _P64, POINTER(c_double),
+                            c_void_p]),
     ("bsm_device_count", c_int, [POINTER(c_int)]),
     ("bsm_malloc", c_int, [c_int, c_size_t, POINTER(c_void_p)]),
     ("bsm_free", c_int, [c_int, c_void_p]),

@@ -352,6 +352,8 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
         if (total_bytes < (int64_t)148 * 16 * (32 << 10))
             pp[0].wsplit_bytes = pp[1].wsplit_bytes = std::max<int64_t>(4 << 10, total_bytes / (148 * 16));
         pp[0].warp_stream = pp[1].warp_stream = H.kind != BSM_KIND_SYMMETRIC;
+        if (opt && (opt->plan_hints & 1)) pp[0].warp_stream = pp[1].warp_stream = false;
+        if (opt && (opt->plan_hints & 2)) pp[0].wsplit_bytes = pp[1].wsplit_bytes = 0;
         if (err.empty()) err = build_plan(H, ir[2], H.nrows, H.ncols, pp[0], H.plan[2]);
         if (err.empty()) err = build_plan(H, ir[3], H.ncols, H.nrows, pp[1], H.plan[3]);
     }

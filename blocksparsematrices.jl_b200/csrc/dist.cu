@@ -442,6 +442,14 @@ int bsm_dist_allreduce_max_f64(bsm_comm c, double *dev_values, int64_t count, vo
     return 0;
 }
 
+int bsm_dist_allreduce_sum_f64(bsm_comm c, double *dev_values, int64_t count, void *stream) {
+    if (!c || !dev_values) return dfail(BSM_ERR_ARG, "null argument");
+    if (c->nranks == 1) return 0;
+    if (int rc = api_ok()) return rc;
+    NCCL_TRY(nccl().AllReduce(dev_values, dev_values, (size_t)count, ncclDouble, ncclSum, c->comm, (cudaStream_t)stream));
+    return 0;
+}
+
 int bsm_mul_dist(bsm_comm c, bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
                  void *x_dev, int64_t ldx, void *y_dev, int64_t ldy, int64_t nrhs, const int64_t *in_cuts,
                  void *stream) {
@@ -477,3 +485,8 @@ int bsm_mul_dist(bsm_comm c, bsm_handle h, int op, const void *alpha, const void
 }
 
 }  // extern "C"
+
+// krylov.cu hook
+int bsm_dist_allreduce_sum_f64_internal(bsm_comm c, double *dev_values, int64_t count, void *stream) {
+    return bsm_dist_allreduce_sum_f64(c, dev_values, count, stream);
+}

@@ -43,7 +43,9 @@ struct alignas(16) TmaHdr {
     int32_t kcv;        // valid contraction entries in this stage (<= 32)
     int32_t mo;         // outputs the block covers (rows for N-form, columns for T-form)
     int32_t ld;         // rows of the stored block (leading dimension of the slab)
-    int32_t flags;      // bit0 T-form, bit1 first stage of a segment, bit2 last stage of a segment, bit3 last stage of the item
+    int32_t flags;      // bit0 T-form, bit1 first stage of a segment, bit2 last stage of a segment, bit3 last stage of the item;
+                        // bits 8..15: offset of the first contraction entry inside the X tile (alignment shift);
+                        // bits 16..23: T-form: first contraction entry (block row) of this stage inside the staged block
     int32_t L;          // rows of the segment
     int32_t out_start;  // first output row if the segment is a contiguous range, else -1
     int64_t out_pool;   // pool offset of the segment's row indices when out_start < 0
@@ -85,8 +87,12 @@ struct TmaGeom {
     static constexpr int S = (int)sizeof(T);
     static constexpr int ABytes = kTMaxM * kTKc * S;          // block slab area (whole 32 x 32 slab)
     static constexpr int ARows = ABytes / 128;                // 128-byte rows of the largest arena box
+    // X area: boxes of 128/S contraction entries x NB columns. The TMA engine needs the global start of a box 16-byte
+    // aligned, so a tile whose first row is not (Float32: xs0 % 4, Float64: xs0 % 2) is fetched from the aligned row
+    // below it and indexed with an offset: Float32 keeps a second box for that, Float64 halves the contraction slab
+    static constexpr int XBoxes = S == 4 ? 2 : kTKc / (128 / S);
     template <int NB>
-    __host__ __device__ static constexpr int XBytes() { return kTKc * NB * S; }
+    __host__ __device__ static constexpr int XBytes() { return XBoxes * NB * 128; }
     template <int NB>
     __host__ __device__ static constexpr int StageBytes() { return ABytes + XBytes<NB>(); }   // multiples of 1 KB: stages stay 1 KB aligned
 };
@@ -130,12 +136,14 @@ __device__ __forceinline__ void spmm_tma_producer(const TmaSpmmArgs<T> &a, const
             const int32_t m = cb.m, n = cb.n;
             const int32_t K = tform ? m : n;          // T-form: m <= 32, one stage holds the whole block
             const int32_t xs0 = __ldg(a.set_start + cb.in_set);
-            for (int32_t k0 = 0; k0 < K; k0 += kTKc) {
-                const int32_t kcv = min(kTKc, K - k0);
+            const int32_t xd = S == 16 ? 0 : (S == 8 ? (xs0 & 1) : (xs0 & 3));      // alignment shift of the X tile
+            const int32_t kstep = (S == 8 && xd) ? kTKc / 2 : kTKc;
+            for (int32_t k0 = 0; k0 < K; k0 += kstep) {
+                const int32_t kcv = min(kstep, K - k0);
                 if (round > 0) mbar_wait(&empty[stage], (round - 1) & 1);
                 unsigned char *sb = smem + stage * G::template StageBytes<NB>();
-                // slab: N-form columns k0 .. k0+kcv (contiguous, 128-byte aligned: 32 columns of m elements);
-                // T-form the whole block
+                // slab: N-form columns k0 .. k0+kcv (contiguous; 16 or 32 columns of m elements start 128-byte
+                // aligned); T-form the whole block (m <= 32), of which this stage contracts rows k0 .. k0+kcv
                 const int64_t boff = (cb.off + (tform ? 0 : (int64_t)k0 * m)) << a.elem_shift;      // bytes, multiple of 128
                 const int32_t slab = (tform ? m * n : m * kcv) << a.elem_shift;
                 const int32_t rows = (slab + 127) >> 7;
@@ -146,17 +154,21 @@ __device__ __forceinline__ void spmm_tma_producer(const TmaSpmmArgs<T> &a, const
                 h.kcv = kcv;
                 h.mo = cb.out_len;
                 h.ld = m;
-                const bool seg_end = (ci == clast) && (k0 + kTKc >= K);
-                h.flags = (tform ? 1 : 0) | (first ? 2 : 0) | (seg_end ? 4 : 0) | ((seg_end && si == s1 - 1) ? 8 : 0);
+                const bool seg_end = (ci == clast) && (k0 + kstep >= K);
+                h.flags = (tform ? 1 : 0) | (first ? 2 : 0) | (seg_end ? 4 : 0) | ((seg_end && si == s1 - 1) ? 8 : 0) |
+                          (xd << 8) | ((tform ? k0 : 0) << 16);
                 h.L = L;
                 h.out_start = ostart;
                 h.out_pool = opool;
                 hdrs[stage] = h;
-                mbar_arrive_expect_tx(&full[stage], abytes + (uint32_t)G::template XBytes<NB>());
+                // only the X boxes that hold valid contraction entries are fetched (the consumers mask the rest)
+                const int32_t nbox = (kcv + xd + KB - 1) / KB;
+                mbar_arrive_expect_tx(&full[stage], abytes + (uint32_t)nbox * (uint32_t)(NB * 128));
                 tma_load_2d(sb, amap + q, 0, (int32_t)(boff >> 7), &full[stage], pol_a);
 #pragma unroll
-                for (int b = 0; b < kTKc / KB; ++b)
-                    tma_load_2d(sb + G::ABytes + b * (NB * 128), xmap, (xs0 + k0 + b * KB) * XE, j0, &full[stage], pol_x);
+                for (int b = 0; b < G::XBoxes; ++b)
+                    if (b < nbox)
+                        tma_load_2d(sb + G::ABytes + b * (NB * 128), xmap, (xs0 + k0 - xd + b * KB) * XE, j0, &full[stage], pol_x);
                 first = false;
                 if (++stage == nst) {
                     stage = 0;
@@ -228,6 +240,7 @@ __device__ __forceinline__ void spmm_tma_stage(const unsigned char *As, const un
     constexpr int S = (int)sizeof(T);
     const int32_t Mt = FULL ? kTMaxM / 8 : (h.L + 7) >> 3;
     const int32_t m = FULL ? kTMaxM : h.ld;
+    const int32_t xd = FULL ? 0 : (h.flags >> 8) & 0xff, kbase = FULL ? 0 : (h.flags >> 16) & 0xff;
     int jcol[LY::NT];
 #pragma unroll
     for (int u = 0; u < LY::NT; ++u) jcol[u] = (LY::NT * 8) * wn + 8 * u + ntile_col<S>(g);
@@ -258,7 +271,7 @@ __device__ __forceinline__ void spmm_tma_stage(const unsigned char *As, const un
             typename FL::V b[LY::NT];
 #pragma unroll
             for (int u = 0; u < LY::NT; ++u) {
-                b[u] = FL::ld(Xs, xtile_index<S, NB>(k, jcol[u]));     // k < 32 always: inside the X area
+                b[u] = FL::ld(Xs, xtile_index<S, NB>(k + xd, jcol[u]));     // k + xd < entries of the X area
                 if (!kv) b[u] = FL::zero();
             }
 #pragma unroll
@@ -267,7 +280,7 @@ __device__ __forceinline__ void spmm_tma_stage(const unsigned char *As, const un
                 if (t < Mt) {      // warp-uniform
                     const int32_t o = 8 * t + g;
                     const bool ok = kv && o < h.mo;
-                    typename FL::V av = FL::ld(As, ok ? swz128<S>(TF ? o * m + k : k * m + o) : 0);
+                    typename FL::V av = FL::ld(As, ok ? swz128<S>(TF ? o * m + kbase + k : k * m + o) : 0);
                     if (!ok) av = FL::zero();
                     if constexpr (S == 16) {
                         if (conj) av.im = -av.im;
@@ -329,7 +342,7 @@ __device__ __forceinline__ void spmm_tma_consumer(const TmaSpmmArgs<T> &a, unsig
 #pragma unroll
                 for (int u = 0; u < LY::NT; ++u) acc[i][u].clear();
         }
-        const bool full = h.kcv == kTKc && h.mo == kTMaxM && h.L == kTMaxM && h.ld == kTMaxM;
+        const bool full = h.kcv == kTKc && h.mo == kTMaxM && h.L == kTMaxM && h.ld == kTMaxM && (h.flags >> 8) == 0;
         if (h.flags & 1) {
             if (full)
                 spmm_tma_stage<T, NB, true, true>(As, Xs, h, a.conj, wm, wn, g, tg, acc);

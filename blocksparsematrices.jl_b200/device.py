@@ -64,7 +64,7 @@ class DeviceMatrix:
     """Opaque handle + size: what `B200(A)` of the Julia extension returns."""
 
     def __init__(self, A: AbstractBlockMatrix, device: int = -1, variant: int = L.VARIANT_AUTO,
-                 own_rows=None, own_cols=None):
+                 own_rows=None, own_cols=None, plan_hints: int = 0):
         lib = L.lib()
         self.host = A
         self.size = A.size
@@ -76,6 +76,7 @@ class DeviceMatrix:
         lib.bsm_default_options(byref(opt))
         opt.device = device
         opt.variant = variant
+        opt.plan_hints = plan_hints
         if own_rows is not None:
             opt.own_row_lo, opt.own_row_hi = int(own_rows[0]), int(own_rows[1])
         if own_cols is not None:
@@ -232,6 +233,23 @@ class DeviceMatrix:
         out = np.zeros(cnt, dt)
         L.check(lib.bsm_table_copy(self._h, table, plan, out.ctypes.data_as(c_void_p), out.nbytes))
         return out
+
+    # ---- solver loop on the device (bsm_cg)
+    def cg(self, b, rtol=1e-10, maxit=200, hermitian=False, check_every=8, stream=None):
+        """Solves A x = b by conjugate gradients kept on the device (hermitian=False: the unconjugated COCG form for
+        complex symmetric operators; the same as CG for real ones). b: CUDA tensor of the operator's dtype.
+        Returns (x, iterations, |r|/|b|)."""
+        import torch
+        if not _is_torch(b) or not b.is_cuda or b.dtype != _torch_dtype(self.dtype) or b.shape != (self.size[0],):
+            raise TypeError("b must be a CUDA vector of the operator's dtype and length")
+        b = b.contiguous()
+        x = torch.empty_like(b)
+        opt = L.CgOptions(rtol, maxit, int(hermitian), check_every)
+        it, rr = c_int64(0), c_double(0.0)
+        st = torch.cuda.current_stream(b.device).cuda_stream if stream is None else stream
+        L.check(L.lib().bsm_cg(self._h, c_void_p(b.data_ptr()), c_void_p(x.data_ptr()), byref(opt), byref(it), byref(rr),
+                               c_void_p(st)))
+        return x, int(it.value), float(rr.value)
 
     # ---- multiply
     def mul(self, op, x, y=None, alpha=True, beta=False, stream=None):

@@ -188,3 +188,19 @@ class SlabMatrix:
                                                c_void_p(y_dev.data_ptr()), y_host_slab.ctypes.data_as(c_void_p),
                                                self.cuts.ctypes.data_as(POINTER(c_int64)), lo, hi, c_void_p(st)))
         return y_host_slab
+
+    def cg(self, b, x, rtol=1e-10, maxit=200, hermitian=False, check_every=8, stream=None):
+        """Collective: conjugate gradients on the sharded operator (bsm_cg_dist). b, x: full-length CUDA tensors of which
+        this rank reads / writes its own rows. Returns (iterations, |r|/|b|)."""
+        import torch
+        from ctypes import c_double
+        D = self.local
+        if b.dtype != _torch_dtype(D.dtype) or x.dtype != b.dtype or b.dim() != 1 or x.shape != b.shape:
+            raise TypeError("b and x must be full-length CUDA vectors of the operator's dtype")
+        opt = L.CgOptions(rtol, maxit, int(hermitian), check_every)
+        it, rr = c_int64(0), c_double(0.0)
+        st = torch.cuda.current_stream(b.device).cuda_stream if stream is None else stream
+        L.check(L.lib().bsm_cg_dist(self.comm._h, D._h, c_void_p(b.data_ptr()), c_void_p(x.data_ptr()),
+                                    self.cuts.ctypes.data_as(POINTER(c_int64)), byref(opt), byref(it), byref(rr),
+                                    c_void_p(st)))
+        return int(it.value), float(rr.value)

@@ -154,7 +154,8 @@ def _fill_block(buf: np.ndarray, seed_key, dtype, symmetric=False):
 
 
 def symmetric_nearfield(seed=2, n=1_000_000, leaf_min=20, leaf_max=200, k_near=6, dtype=np.complex128,
-                        permuted=False, threads=8, leaves=None, return_structure=False, scattered=False):
+                        permuted=False, threads=8, leaves=None, return_structure=False, scattered=False,
+                        diag_shift=0.0):
     """C2: BEM near-field style SymmetricBlockMatrix. Leaves ~U{leaf_min..leaf_max} tile the n unknowns;
     every leaf has a (symmetrised) diagonal block; every leaf i >= 1 has ONE half-stored off-diagonal
     block whose rows are the leaf and whose columns are the union of min(i, k_near) lower-numbered
@@ -162,6 +163,8 @@ def symmetric_nearfield(seed=2, n=1_000_000, leaf_min=20, leaf_max=200, k_near=6
     the reference's cuboid/sphere fixture). With the defaults: ~9.1k leaves, ~12.7 GB of ComplexF64.
     permuted=True applies a random renumbering of the unknowns (arbitrary index vectors, as the reference's
     fixture has); scattered=True draws the near leaves from ALL lower-numbered leaves instead of a band.
+    diag_shift is added to the diagonal of every diagonal block (a shift of a few hundred makes the operator well
+    conditioned — definite enough for the CG / COCG solver loop — without changing its structure).
     Block values come from per-block seeds, so `leaves=(lo, hi)` materialises exactly the blocks the
     slab owning leaves [lo, hi) needs (its diagonal blocks, its off-diagonal rows, and the blocks of
     other leaves whose column set touches the slab) with the same values as in the full matrix."""
@@ -202,6 +205,9 @@ def symmetric_nearfield(seed=2, n=1_000_000, leaf_min=20, leaf_max=200, k_near=6
     else:
         for j in jobs:
             work(j)
+    if diag_shift:
+        for d in diag:
+            d[np.diag_indices(d.shape[0])] += diag_shift
     A = SymmetricBlockMatrix(diag, [lidx(i) for i in dsel], off, [lidx(i) for i in osel],
                              [np.concatenate([lidx(j) for j in near[i]]) for i in osel], (n, n))
     return (A, S) if return_structure else A

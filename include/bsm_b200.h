@@ -84,7 +84,10 @@ typedef struct {
      * rows), own_col_* to op T/C (outputs are columns). */
     int64_t own_row_lo, own_row_hi;
     int64_t own_col_lo, own_col_hi;
-    int64_t reserved[4];
+    int64_t plan_hints;    /* 0 = automatic. Bits, for experiments and comparison runs: 1 = short segments go to the CTA-stream
+                              kernel, not the warp-stream kernel; 2 = never cut the segments of a small (L2-resident) problem
+                              into per-block work items (no partial sums, single launch) */
+    int64_t reserved[3];
 } bsm_options;
 
 void bsm_default_options(bsm_options *opt);
@@ -288,6 +291,7 @@ int bsm_dist_info(bsm_comm c, int *nranks, int *rank, int *nccl_version);
 int bsm_dist_allgather_rows(bsm_comm c, int dtype, void *x_dev, int64_t ldx, int64_t nrhs, const int64_t *cuts,
                             void *stream);
 int bsm_dist_allreduce_max_f64(bsm_comm c, double *dev_values, int64_t count, void *stream);
+int bsm_dist_allreduce_sum_f64(bsm_comm c, double *dev_values, int64_t count, void *stream);
 /* Peer mode — the all-gather fused into the multiply. bsm_dist_alloc is collective: every rank allocates `bytes`
  * on its GPU and maps every peer's allocation (CUDA IPC, NVLink peer access). Keep a full-length x in such an
  * array; a rank only ever writes its own slab. bsm_mul_dist_peer (nrhs = 1) runs NO collective and launches NO
@@ -312,6 +316,32 @@ int bsm_mul_dist_peer_host(bsm_comm c, bsm_handle h, int op, const void *alpha, 
 int bsm_mul_dist(bsm_comm c, bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
                  void *x_dev, int64_t ldx, void *y_dev, int64_t ldy, int64_t nrhs, const int64_t *in_cuts,
                  void *stream);
+
+/* ---- solver loop on the device ----------------------------------------------------
+ * The reference is an operator for Krylov solvers driven through LinearMaps (docs/src/block.md:56-63 times the three
+ * products they are built from); bsm_cg keeps such a loop on the GPU: conjugate gradients for A x = b, x0 = 0, with
+ * the Hermitian inner product (hermitian != 0: CG, Hermitian positive definite operators) or the unconjugated
+ * bilinear form (hermitian = 0: COCG, for the complex SYMMETRIC operators a SymmetricBlockMatrix{ComplexF64} holds;
+ * the same as CG for real dtypes). Per iteration: one bsm_mul (q = A p) and three fused vector kernels
+ * (p.q | x += alpha p, r -= alpha q, r.r, |r|^2 | p = r + beta p); alpha, beta and the residual history stay on the
+ * device, the host synchronises once per `check_every` iterations; reductions use a fixed number of partial sums and
+ * fixed trees (bitwise reproducible). Stops when |r| <= rtol * |b| or after maxit iterations; returns the iterations
+ * run and the last |r| / |b|.
+ * bsm_cg_dist: the operator is sharded into block-row slabs (slab handle + communicator, cuts as in
+ * bsm_mul_dist_peer); b_dev / x_dev are full-length device arrays of which this rank reads / writes rows
+ * cuts[rank] .. cuts[rank+1]; the search direction lives in a peer-mapped array the peers read over NVLink, the two
+ * dot products per iteration are summed over the ranks with ncclAllReduce. Collective. */
+typedef struct {
+    double rtol;
+    int64_t maxit;
+    int32_t hermitian;
+    int32_t check_every;
+} bsm_cg_options;
+void bsm_cg_default_options(bsm_cg_options *opt);   /* rtol 1e-10, maxit 200, hermitian 0, check_every 8 */
+int bsm_cg(bsm_handle h, const void *b_dev, void *x_dev, const bsm_cg_options *opt, int64_t *iters, double *relres,
+           void *stream);
+int bsm_cg_dist(bsm_comm c, bsm_handle h, const void *b_dev, void *x_dev, const int64_t *cuts, const bsm_cg_options *opt,
+                int64_t *iters, double *relres, void *stream);
 
 /* ---- device memory helpers for callers without a CUDA array package ------------------------ */
 int bsm_device_count(int *count);

@@ -58,17 +58,23 @@ static int conflict_degree(const int (&byteaddr)[32]) {
     return worst;
 }
 
+// xs0: first row of X the block multiplies (its alignment decides the shifted fetch of the X tile)
 template <int S, int NB>
-static int run_case(int m, int n, bool tform, int L, bool conj, int *worstA, int *worstB) {
+static int run_case(int m, int n, bool tform, int L, bool conj, int xs0, int *worstA, int *worstB) {
     using T = typename Elem<S>::T;
     using W = typename Elem<S>::W;
     constexpr int NT = NB >= 16 ? 2 : 1, WN = NB >= 16 ? NB / 16 : 1, WM = 4 / WN, MT = (4 + WM - 1) / WM;
     constexpr int KB = 128 / S;
     const int K = tform ? m : n;             // contraction length (T-form: m <= 32)
     const int mo = tform ? n : m;            // outputs of the block
-    std::vector<T> B((size_t)m * n), X((size_t)K * NB);
+    constexpr int XBoxes = S == 4 ? 2 : 32 / KB;
+    std::vector<T> B((size_t)m * n), X((size_t)K * NB), Xglob((size_t)(xs0 + K + 64) * NB);
     for (auto &v : B) v = rnd<T>();
-    for (auto &v : X) v = rnd<T>();
+    for (auto &v : Xglob) v = rnd<T>();                      // rows around the block's range hold other data
+    for (int j = 0; j < NB; ++j)
+        for (int k = 0; k < K; ++k) X[(size_t)j * K + k] = Xglob[(size_t)j * (xs0 + K + 64) + xs0 + k];
+    const int xd = S == 16 ? 0 : (S == 8 ? (xs0 & 1) : (xs0 & 3));
+    const int kstep = (S == 8 && xd) ? 16 : 32;
     std::vector<W> ref((size_t)L * NB, W(0)), out((size_t)L * NB, W(0));
     for (int o = 0; o < mo; ++o)
         for (int j = 0; j < NB; ++j) {
@@ -82,23 +88,28 @@ static int run_case(int m, int n, bool tform, int L, bool conj, int *worstA, int
         }
     // stages of 32 contraction entries
     std::vector<W> accs((size_t)4 * MT * NT * 64, W(0));   // [warp][i][u][g][n]
-    for (int k0 = 0; k0 < K; k0 += 32) {
-        const int kcv = std::min(32, K - k0);
-        std::vector<unsigned char> As(32 * 32 * S + 1024, 0xA5), Xs((size_t)32 * NB * S, 0x5A);
+    for (int k0 = 0; k0 < K; k0 += kstep) {
+        const int kcv = std::min(kstep, K - k0);
+        const int kbase = tform ? k0 : 0;
+        std::vector<unsigned char> As(32 * 32 * S + 1024, 0xA5), Xs((size_t)XBoxes * NB * 128, 0x5A);
         const size_t slab_bytes = (size_t)(tform ? m * n : m * kcv) * S;
         tma_place_linear(As, 0, reinterpret_cast<const unsigned char *>(B.data() + (tform ? 0 : (size_t)k0 * m)), slab_bytes);
-        // X boxes: KB contraction entries x NB columns each; rows past K are "other data" (here: garbage 0x5A stays)
-        for (int b = 0; b < 32 / KB; ++b)
+        // X boxes: KB contraction entries x NB columns each, fetched from the 16-byte aligned row xs0 + k0 - xd; only
+        // the boxes that hold valid entries are fetched (the others keep stale bytes)
+        const int nbox = (kcv + xd + KB - 1) / KB;
+        if (nbox > XBoxes) { std::printf("X area too small\n"); return 1; }
+        if (((size_t)(xs0 + k0 - xd) * S) % 16 != 0) { std::printf("misaligned X fetch\n"); return 1; }
+        if (((size_t)(tform ? 0 : k0) * m * S) % 128 != 0) { std::printf("misaligned slab\n"); return 1; }
+        for (int b = 0; b < nbox; ++b)
             for (int j = 0; j < NB; ++j)
                 for (int kk = 0; kk < KB; ++kk) {
-                    const int k = k0 + b * KB + kk;
-                    if (k >= K) continue;
+                    const int grow = xs0 + k0 - xd + b * KB + kk;
                     const size_t bytepos = (size_t)kk * S;
                     const size_t chunk = bytepos >> 4;
                     const size_t dst = (size_t)b * (NB * 128) + (size_t)j * 128 + ((chunk ^ (j & 7)) << 4) + (bytepos & 15);
-                    std::memcpy(&Xs[dst], &X[(size_t)j * K + k], S);
+                    std::memcpy(&Xs[dst], &Xglob[(size_t)j * (xs0 + K + 64) + grow], S);
                 }
-        const bool full = kcv == 32 && mo == 32 && L == 32 && m == 32;
+        const bool full = kcv == 32 && mo == 32 && L == 32 && m == 32 && xd == 0;
         const int Mt = (L + 7) >> 3;
         for (int warp = 0; warp < 4; ++warp) {
             const int wn = warp % WN, wm = warp / WN;
@@ -113,7 +124,7 @@ static int run_case(int m, int n, bool tform, int L, bool conj, int *worstA, int
                     const bool kv = k < kcv;
                     for (int u = 0; u < NT; ++u) {
                         const int j = NT * 8 * wn + 8 * u + ntile_col<S>(g);
-                        const int idx = xtile_index<S, NB>(k, j);
+                        const int idx = xtile_index<S, NB>(k + xd, j);
                         baddr[u][lane] = idx * S;
                         T v;
                         std::memcpy(&v, &Xs[(size_t)idx * S], S);
@@ -124,7 +135,7 @@ static int run_case(int m, int n, bool tform, int L, bool conj, int *worstA, int
                         tile_on[i] = t < Mt;
                         const int o = 8 * t + g;
                         const bool ok = kv && o < mo && t < Mt;
-                        const int idx = ok ? swz128<S>(tform ? o * m + k : k * m + o) : 0;
+                        const int idx = ok ? swz128<S>(tform ? o * m + kbase + k : k * m + o) : 0;
                         aaddr[i][lane] = idx * S;
                         T v;
                         std::memcpy(&v, &As[(size_t)idx * S], S);
@@ -181,10 +192,11 @@ template <int S, int NB>
 static int run_all() {
     int bad = 0, wa = 1, wb = 1;
     const int shapes[][3] = {{32, 32, 32}, {32, 70, 32}, {24, 17, 24}, {8, 8, 8}, {5, 3, 7}, {32, 1, 32}, {17, 32, 32}, {1, 1, 1}, {31, 33, 31}};
-    for (auto &sh : shapes) {
-        bad += run_case<S, NB>(sh[0], sh[1], false, sh[2], false, &wa, &wb);
-        if (sh[1] <= 32) bad += run_case<S, NB>(sh[0], sh[1], true, std::max(sh[1], 1), S == 16, &wa, &wb);
-    }
+    for (auto &sh : shapes)
+        for (int xs0 = 0; xs0 < 4; ++xs0) {
+            bad += run_case<S, NB>(sh[0], sh[1], false, sh[2], false, xs0, &wa, &wb);
+            if (sh[1] <= 32) bad += run_case<S, NB>(sh[0], sh[1], true, std::max(sh[1], 1), S == 16, xs0, &wa, &wb);
+        }
     std::printf("S=%d NB=%d worst conflict degree on full slabs: A %d, B %d\n", S, NB, wa, wb);
     return bad;
 }

@@ -485,3 +485,23 @@ def test_sparse_on_device_other_types():
     # empty matrix
     Es = B.BlockSparseMatrix([], [], [], (7, 5)).device().sparse("N")
     assert Es.shape == (7, 5) and Es.nnz == 0
+
+
+# ---- solver loop on the device (bsm_cg) ------------------------------------------------------
+@pytest.mark.parametrize("dtype,hermitian", [(np.float64, False), (np.complex128, False), (np.float32, False), (np.float64, True)])
+def test_cg_through_the_operator(dtype, hermitian):
+    """CG (real symmetric) / COCG (complex symmetric) kept on the device: the solution must satisfy A x = b to the
+    requested tolerance when the residual is recomputed with the ORACLE's multiply, and two runs must agree bitwise."""
+    import torch
+    A = G.symmetric_nearfield(seed=61, n=20000, k_near=4, dtype=dtype, diag_shift=300.0 if dtype != np.complex128 else 300.0 + 60.0j)
+    D = A.device()
+    rng = np.random.default_rng(9)
+    b = randx(rng, A.size[0], dtype)
+    rtol = 1e-4 if dtype == np.float32 else 1e-10
+    x, it, rel = D.cg(torch.from_numpy(b).cuda(), rtol=rtol, maxit=100, hermitian=hermitian)
+    assert 2 <= it < 60 and rel <= rtol, (it, rel)
+    xh = x.cpu().numpy()
+    res = oracle_mul(A, xh, "N", f64=(dtype == np.float32)) - b
+    assert np.linalg.norm(res) / np.linalg.norm(b) < (5e-4 if dtype == np.float32 else 5e-10)
+    x2, it2, rel2_ = D.cg(torch.from_numpy(b).cuda(), rtol=rtol, maxit=100, hermitian=hermitian)
+    assert it2 == it and torch.equal(x, x2)
