@@ -79,6 +79,7 @@ SIGNATURES = [
     ("bsm_dist_set_overlap", c_int, [c_void_p, c_int]),
     ("bsm_dist_set_collective", c_int, [c_void_p, c_int]),
     ("bsm_dist_set_debug", c_int, [c_void_p, c_int]),
+    ("bsm_dist_debug_read", c_int, [c_void_p, _P64]),
     ("bsm_dist_info", c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     ("bsm_dist_allgather_rows", c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64, _P64, c_void_p]),
     ("bsm_dist_allreduce_max_f64", c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

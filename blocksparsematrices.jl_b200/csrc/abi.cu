@@ -354,6 +354,7 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
         pp[0].warp_stream = pp[1].warp_stream = H.kind != BSM_KIND_SYMMETRIC;
         if (opt && (opt->plan_hints & 1)) pp[0].warp_stream = pp[1].warp_stream = false;
         if (opt && (opt->plan_hints & 2)) pp[0].wsplit_bytes = pp[1].wsplit_bytes = 0;
+        if (opt && (opt->plan_hints & 4)) pp[0].wcta = pp[1].wcta = false;
         if (err.empty()) err = build_plan(H, ir[2], H.nrows, H.ncols, pp[0], H.plan[2]);
         if (err.empty()) err = build_plan(H, ir[3], H.ncols, H.nrows, pp[1], H.plan[3]);
     }
@@ -604,6 +605,9 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
     const int32_t g0 = phase == 2 ? (int32_t)HP.n_gather_local : 0;
     const int32_t g1 = phase == 3 ? 0 : phase == 1 ? (int32_t)HP.n_gather_local : ngather_all;
     constexpr int VMAX = 16 / (int)sizeof(T);
+    // CTA-part plans whose only leftover work is "rows no block touches": folded into the warp-stream launch
+    const bool fold_zero_rows = HP.wcta && HP.scratch_elems == 0 && phase == 0 && nfused == 0 && ngather_all == 0 &&
+                                nitems_all > 0 && !HP.gather_rows.empty();
     if (p >= 4) {
         // colour-ordered variant: y <- beta*y, then one launch per (sweep, colour); the slices of a launch
         // touch disjoint rows, so each accumulates straight into y (beta = 1), as the reference's tasks do
@@ -731,6 +735,7 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             a.x.sync.do_exit = 0;
             a.x.sync.arrivals = 1;
             a.x.sync.debug = px->debug;
+            a.x.sync.dbg = px->dbg;
             if (last_kind < 0) {   // nothing to multiply on this rank: the barriers alone
                 PeerSync ps = a.x.sync;
                 ps.do_exit = 1;
@@ -781,11 +786,19 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             w.nitems = w1 - w0;
             w.beta_false = a.beta_false;
             w.conj = a.conj;
+            w.cta_mode = HP.wcta ? 1 : 0;
+            w.nz = 0;
+            w.zrows = nullptr;
+            if (fold_zero_rows) {   // single launch: the rows no block touches are set by extra CTAs of this kernel
+                w.nz = (int32_t)HP.gather_rows.size();
+                w.zrows = DP.gather_rows.p;
+            }
             if (w.x.npeer && last_kind == 1) {
                 w.x.sync.do_exit = 1;
                 w.x.sync.arrivals = (int32_t)((w.nitems + kWWarps - 1) / kWWarps) * kWWarps;
             }
-            stream_warp_kernel<T><<<(unsigned)((w.nitems + kWWarps - 1) / kWWarps), kWWarps * 32,
+            const unsigned zctas = (unsigned)((w.nz + kWWarps * 32 - 1) / (kWWarps * 32));
+            stream_warp_kernel<T><<<(unsigned)((w.nitems + kWWarps - 1) / kWWarps) + zctas, kWWarps * 32,
                                     stream_warp_smem_bytes<T>(), st>>>(w);
             CUDA_TRY(cudaGetLastError());
         }
@@ -801,7 +814,7 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             CUDA_TRY(cudaGetLastError());
         }
         if (prof) CUDA_TRY(cudaEventRecord(A->ev[1], st));
-        const int64_t ng = (phase == 1 || phase == 2) ? 0 : (int64_t)HP.gather_rows.size();
+        const int64_t ng = (phase == 1 || phase == 2 || fold_zero_rows) ? 0 : (int64_t)HP.gather_rows.size();
         if (ng > 0) {
             FinalizeArgs<T> f;
             f.rows = DP.gather_rows.p;
@@ -1351,8 +1364,10 @@ int bsm_launch_count(bsm_handle h, int op) {
     if (!h || op < BSM_OP_N || op > BSM_OP_C) return BSM_ERR_ARG;
     const HostPlan &P = h->H.plan[plan_index(h, op)];
     if (P.color_ok) return (int)P.color_ptr.size();      // scale kernel + one launch per (sweep, colour)
+    const bool only_warp = P.n_fused_slices == 0 && (int64_t)P.slices.size() == P.n_warp_slices && P.n_warp_slices > 0;
+    const bool folded = P.wcta && P.scratch_elems == 0 && only_warp;      // zero rows set inside the warp-stream launch
     return (P.n_fused_slices > 0 ? 1 : 0) + (P.n_warp_slices > 0 ? 1 : 0) +
-           ((int64_t)P.slices.size() > P.n_fused_slices + P.n_warp_slices ? 1 : 0) + (P.gather_rows.empty() ? 0 : 1);
+           ((int64_t)P.slices.size() > P.n_fused_slices + P.n_warp_slices ? 1 : 0) + ((P.gather_rows.empty() || folded) ? 0 : 1);
 }
 
 }  // extern "C"

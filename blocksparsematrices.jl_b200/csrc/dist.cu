@@ -283,6 +283,16 @@ int bsm_dist_set_debug(bsm_comm c, int flags) {
     return 0;
 }
 
+int bsm_dist_debug_read(bsm_comm c, int64_t out[8]) {
+    if (!c || !out) return dfail(BSM_ERR_ARG, "null argument");
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    if (!c->sync_state) return 0;
+    if (cudaMemcpy(out, c->sync_state + 8, sizeof(long long) * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemset(c->sync_state + 8, 0, sizeof(long long) * 8) != cudaSuccess)
+        return dfail(BSM_ERR_CUDA, "reading the barrier timers failed");
+    return 0;
+}
+
 int bsm_dist_set_collective(bsm_comm c, int use_broadcasts) {
     if (!c) return dfail(BSM_ERR_ARG, "null communicator");
     c->use_broadcasts = use_broadcasts ? 1 : 0;
@@ -335,10 +345,11 @@ int ensure_flags(bsm_comm c) {
     if (int rc = shared_alloc(c, sizeof(int32_t) * 2 * (size_t)c->nranks, &sh)) return rc;
     c->shared.push_back(sh);
     if (cudaMalloc(&c->peer_flags_dev, sizeof(int32_t *) * 8) != cudaSuccess ||
-        cudaMalloc(&c->sync_state, sizeof(int32_t) * 4) != cudaSuccess)
+        cudaMalloc(&c->sync_state, sizeof(int32_t) * 8 + sizeof(long long) * 8) != cudaSuccess)
         return dfail(BSM_ERR_ALLOC, "cudaMalloc failed");
     if (cudaMemcpy(c->peer_flags_dev, sh.peer, sizeof(void *) * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemset(c->sync_state, 0, sizeof(int32_t) * 4) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+        cudaMemset(c->sync_state, 0, sizeof(int32_t) * 8 + sizeof(long long) * 8) != cudaSuccess ||
+        cudaDeviceSynchronize() != cudaSuccess)
         return dfail(BSM_ERR_CUDA, "initialising the barrier state failed");
     c->flags = (int32_t *)sh.local;   // set last: a failed setup is retried, never half-used
     return 0;
@@ -400,6 +411,7 @@ int bsm_mul_dist_peer(bsm_comm c, bsm_handle h, int op, const void *alpha, const
     px.state = c->sync_state;
     px.rank = c->rank;
     px.debug = c->debug;
+    px.dbg = reinterpret_cast<long long *>(c->sync_state + 8);
     void *scratch = nullptr;
     return bsm_mul_phase(h, op, alpha, beta, beta_is_false, x_shared, y_dev, stream, 0, &scratch, &px);
 }

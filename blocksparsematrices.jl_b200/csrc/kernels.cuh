@@ -118,8 +118,17 @@ struct PeerSync {
     int32_t do_exit;      // this kernel runs the exit barrier
     int32_t arrivals;     // arrivals the exit barrier expects
     int32_t debug;        // benchmarking only (bsm_dist_set_debug): bit0 skip the entry wait, bit1 skip the exit wait,
-                          // bit2 every arrival does the system-scope wait itself
+                          // bit2 every arrival does the system-scope wait itself, bit3 record %globaltimer stamps in dbg
+                          // (sums over the multiplies: [0] entry wait ns, [1] kernel start -> last arrival ns,
+                          // [2] exit wait ns, [3] count), bit4 signal with relaxed instead of release stores
+    long long *dbg;
 };
+
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ int32_t ld_acquire_sys(const int32_t *p) {
     int32_t v;
@@ -151,24 +160,42 @@ __device__ __forceinline__ void st_release_gpu(int32_t *p, int32_t v) {
 // is still behind; it then publishes the epoch in state[3] with a device-scope release, and everybody else gets by
 // with ONE device-scope acquire of that local word (the synchronisation chain peer -> first arrival -> this thread
 // is transitive).
+__device__ __forceinline__ void peer_signal(const PeerSync &s, int32_t *flag, int32_t e) {
+    if (s.debug & 16)
+        *reinterpret_cast<volatile int32_t *>(flag) = e;
+    else
+        st_release_sys(flag, e);
+}
 __device__ __forceinline__ void peer_entry(const PeerSync &s) {
     const int32_t e = *reinterpret_cast<volatile int32_t *>(s.state) + 1;
     if (*reinterpret_cast<volatile int32_t *>(s.state + 1) < e && atomicMax(s.state + 1, e) < e) {
-        for (int p = 0; p < s.nranks; ++p) st_release_sys(s.peer_flags[p] + s.rank, e);
+        if (s.debug & 8) s.dbg[4] = global_ns();
+        for (int p = 0; p < s.nranks; ++p) peer_signal(s, s.peer_flags[p] + s.rank, e);
     }
     if (s.debug & 1) return;
     if (!(s.debug & 4) && ld_acquire_gpu(s.state + 3) >= e) return;
     for (int p = 0; p < s.nranks; ++p) peer_spin(s.my_flags + p, e);
-    if (!(s.debug & 4)) st_release_gpu(s.state + 3, e);
+    if (!(s.debug & 4)) {
+        if ((s.debug & 8) && atomicMax(s.state + 4, e) < e) s.dbg[5] = global_ns();
+        st_release_gpu(s.state + 3, e);
+    }
 }
 __device__ __forceinline__ void peer_exit(const PeerSync &s) {
     if (!s.do_exit) return;
     __threadfence();
     if (atomicAdd(s.state + 2, 1) != s.arrivals - 1) return;
     const int32_t e = *reinterpret_cast<volatile int32_t *>(s.state) + 1;
-    for (int p = 0; p < s.nranks; ++p) st_release_sys(s.peer_flags[p] + s.nranks + s.rank, e);
+    const long long t2 = (s.debug & 8) ? global_ns() : 0;
+    for (int p = 0; p < s.nranks; ++p) peer_signal(s, s.peer_flags[p] + s.nranks + s.rank, e);
     if (!(s.debug & 2))
         for (int p = 0; p < s.nranks; ++p) peer_spin(s.my_flags + s.nranks + p, e);
+    if (s.debug & 8) {
+        const long long t3 = global_ns();
+        s.dbg[0] += s.dbg[5] - s.dbg[4];
+        s.dbg[1] += t2 - s.dbg[4];
+        s.dbg[2] += t3 - t2;
+        s.dbg[3] += 1;
+    }
     *reinterpret_cast<volatile int32_t *>(s.state + 2) = 0;
     *reinterpret_cast<volatile int32_t *>(s.state) = e;
     __threadfence();
@@ -889,6 +916,12 @@ struct WarpArgs {
     int32_t nitems;
     int32_t beta_false;
     int32_t conj;
+    // CTA-part mode (small problems, plan.h HostPlan::wcta): the 4 items of a CTA are parts of ONE segment; their
+    // partial vectors meet in shared memory and warp 0 writes the outputs. CTAs past the item CTAs set the rows no
+    // block touches (zrows) to beta*y, so that the whole multiply is a single launch.
+    int32_t cta_mode;
+    int32_t nz;
+    const int32_t *zrows;
 };
 
 struct WDesc {
@@ -1063,7 +1096,7 @@ __device__ __forceinline__ void wchunk_compute(const T *__restrict__ sm, const T
 template <class T, bool CONJ>
 __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned char *ring, const int4 *dring,
                                                  T *xs, T *ts, uint64_t *full, uint64_t *dbar, int32_t q0,
-                                                 int32_t n) {
+                                                 int32_t n, T *cta_part, uint32_t &end_fl, int64_t &end_out, int32_t &end_L) {
     const int lane = threadIdx.x & 31;
     const uint64_t policy = l2_evict_first_policy();
     const int32_t nbatch = (n + kWDBatch - 1) / kWDBatch;
@@ -1172,7 +1205,12 @@ __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned 
                 const int32_t r = lane + 32 * h;
                 if (r < L) {
                     const T tot = El<T>::add(h ? acc1 : acc0, ts[r]);
-                    if (fl & 32u) {
+                    if (fl & 64u) {          // part of a segment: the CTA sums the parts (stream_warp_kernel)
+                        cta_part[r] = tot;
+                        end_fl = fl;
+                        end_out = o;
+                        end_L = L;
+                    } else if (fl & 32u) {
                         const int32_t row = (fl & 4u) ? __ldg(a.pool + o + r) : (int32_t)o + r;
                         T v = El<T>::mul(a.alpha, tot);
                         if (!a.beta_false) v = El<T>::add(v, El<T>::mul(a.beta, a.y[row]));
@@ -1195,18 +1233,33 @@ __host__ __device__ constexpr size_t stream_warp_smem_per_warp() {
 }
 template <class T>
 constexpr size_t stream_warp_smem_bytes() {
-    return kWWarps * stream_warp_smem_per_warp<T>();
+    return kWWarps * stream_warp_smem_per_warp<T>() + kWWarps * kWSegMax * sizeof(T) + 16;   // + the parts of CTA-part mode
 }
 
 template <class T>
 __global__ void __launch_bounds__(kWWarps * 32) stream_warp_kernel(const WarpArgs<T> a) {
     extern __shared__ __align__(128) unsigned char wsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int32_t nctas = (a.nitems + kWWarps - 1) / kWWarps;
+    if ((int32_t)blockIdx.x >= nctas) {   // rows no block touches: y <- beta*y (these CTAs exist in CTA-part mode only)
+        const int32_t i = ((int32_t)blockIdx.x - nctas) * (kWWarps * 32) + (int32_t)threadIdx.x;
+        if (i < a.nz) {
+            const int32_t row = __ldg(a.zrows + i) & 0x7fffffff;
+            a.y[row] = a.beta_false ? El<T>::zero() : El<T>::mul(a.beta, a.y[row]);
+        }
+        return;
+    }
     const int32_t item = blockIdx.x * kWWarps + warp;
     if (a.x.npeer) {   // every warp is its own pipeline: one arrival per warp
         if (lane == 0) peer_entry(a.x.sync);
         __syncwarp();
     }
+    T *parts = reinterpret_cast<T *>(wsm + kWWarps * stream_warp_smem_per_warp<T>());
+    int32_t *valid = reinterpret_cast<int32_t *>(parts + kWWarps * kWSegMax);
+    uint32_t end_fl = 0;
+    int64_t end_out = 0;
+    int32_t end_L = 0;
+    bool has_work = false;
     if (item < a.nitems) {
         unsigned char *base = wsm + warp * stream_warp_smem_per_warp<T>();
         unsigned char *ring = base;
@@ -1223,10 +1276,38 @@ __global__ void __launch_bounds__(kWWarps * 32) stream_warp_kernel(const WarpArg
         __syncwarp();
         const int32_t q0 = __ldg(a.item_ptr + item), q1 = __ldg(a.item_ptr + item + 1);
         if (q0 < q1) {
+            has_work = true;
             if (a.conj)
-                stream_warp_body<T, true>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0);
+                stream_warp_body<T, true>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0, parts + warp * kWSegMax, end_fl,
+                                          end_out, end_L);
             else
-                stream_warp_body<T, false>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0);
+                stream_warp_body<T, false>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0, parts + warp * kWSegMax, end_fl,
+                                           end_out, end_L);
+        }
+    }
+    if (a.cta_mode) {
+        // the parts of the segment meet here: fixed order (warp 0, 1, 2, 3), one writer
+        if (lane == 0) valid[warp] = has_work ? 1 : 0;
+        __syncthreads();
+        if (warp == 0 && has_work) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int32_t r = lane + 32 * h;
+                if (r < end_L) {
+                    T tot = parts[r];
+#pragma unroll
+                    for (int w = 1; w < kWWarps; ++w)
+                        if (valid[w]) tot = El<T>::add(tot, parts[w * kWSegMax + r]);
+                    if (end_fl & 32u) {
+                        const int32_t row = (end_fl & 4u) ? __ldg(a.pool + end_out + r) : (int32_t)end_out + r;
+                        T v = El<T>::mul(a.alpha, tot);
+                        if (!a.beta_false) v = El<T>::add(v, El<T>::mul(a.beta, a.y[row]));
+                        a.y[row] = v;
+                    } else {
+                        a.scratch[end_out + r] = tot;
+                    }
+                }
+            }
         }
     }
     if (a.x.npeer) {

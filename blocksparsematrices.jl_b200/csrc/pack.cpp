@@ -213,6 +213,25 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
     std::vector<Tmp> tmp;
     std::vector<uint8_t> group_warp(G, 0);
     const int64_t hmin = std::max<int64_t>(1, 128 / s);
+    // whether group g is streamed by the warp-stream kernel (whole segment of <= kWarpMaxRows rows, short blocks)
+    auto warp_eligible = [&](size_t g) -> bool {
+        const int64_t L = S.len[gset[g]];
+        if (!(pp.fused && pp.warp_stream) || L == 0 || L > kWarpMaxRows || S.pool.size() >= (size_t)0x7fffffff) return false;
+        int64_t entries = 0;
+        for (int64_t c = P.group_ptr[g]; c < P.group_ptr[g + 1]; ++c) {
+            const bsm_contrib &cb = P.contrib[c];
+            entries += (int64_t)cb.m * cb.n;
+            if (contrib_tset[(size_t)c] >= 0 || cb.m > kWarpMaxRows) return false;
+        }
+        return entries > 0;
+    };
+    // small (L2-resident, latency-bound) problems with few segments: CTA-part mode instead of per-block work items
+    // with partial sums through scratch + a second launch
+    if (pp.wsplit_bytes > 0 && pp.wcta && pp.in_hi < 0) {
+        int64_t nw = 0;
+        for (size_t g = 0; g < G; ++g) nw += warp_eligible(g) ? 1 : 0;
+        P.wcta = nw > 0 && nw <= kWCtaMaxSegments;
+    }
     for (size_t g = 0; g < G; ++g) {
         const int64_t L = S.len[gset[g]];
         if (L == 0) continue;
@@ -243,7 +262,7 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
             // a segment with several blocks into several work items: the first stays direct, the others
             // deliver partial vectors through the gather lists
             group_warp[g] = 1;
-            const int64_t budget = pp.wsplit_bytes > 0 ? pp.wsplit_bytes : (int64_t)1 << 62;
+            const int64_t budget = (pp.wsplit_bytes > 0 && !P.wcta) ? pp.wsplit_bytes : (int64_t)1 << 62;
             int32_t cb0 = (int32_t)P.group_ptr[g];
             const int32_t cend = (int32_t)P.group_ptr[g + 1];
             bool first_item = true;
@@ -529,21 +548,56 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
                 }
             }
             if (P.wchunk.size() == first) return "warp-stream segment without data";
+            // output of the segment: the same record closes the segment (or every part of it)
+            uint8_t out_flags = 0;
+            int64_t out_ref;
+            if (sl.flags & kSliceDirect) {
+                out_flags |= kWcDirect;
+                if (S.start[sl.out_set] < 0) {
+                    out_flags |= kWcOutPool;
+                    out_ref = S.pool_off[sl.out_set];
+                } else {
+                    out_ref = S.start[sl.out_set];
+                }
+            } else {
+                out_ref = sl.scratch_off;
+            }
+            if (P.wcta) {
+                // CTA-part mode: the chunk list of the segment is dealt to kWItemsPerCta consecutive work items (the
+                // warps of one CTA), balanced by bytes; part 0 is never empty, later parts may be
+                const size_t last = P.wchunk.size();
+                int64_t seg_bytes = 0;
+                for (size_t q = first; q < last; ++q) seg_bytes += (int64_t)P.wchunk[q].bytes16 * 16;
+                size_t q = first;
+                int64_t done = 0;
+                for (int part = 0; part < kWItemsPerCta; ++part) {
+                    const size_t q_begin = q;
+                    const int64_t goal = seg_bytes * (part + 1) / kWItemsPerCta;
+                    if (part == kWItemsPerCta - 1) {
+                        q = last;
+                    } else {
+                        while (q < last && done < goal) {
+                            done += (int64_t)P.wchunk[q].bytes16 * 16;
+                            ++q;
+                        }
+                    }
+                    if (q > q_begin) {
+                        P.wchunk[q_begin].flags |= kWcSegBegin;
+                        bsm_wchunk &pe = P.wchunk[q - 1];
+                        pe.flags |= kWcSegEnd | kWcCtaPart | out_flags;
+                        pe.out = out_ref;
+                    }
+                    P.witem_ptr.push_back((int32_t)q);
+                }
+                if (q != last) return "CTA-part split lost chunks";
+                if (!(sl.flags & kSliceRemote)) P.n_warp_items_local = (int64_t)P.witem_ptr.size() - 1;
+                continue;
+            }
             bsm_wchunk &wb = P.wchunk[first];
             bsm_wchunk &we = P.wchunk.back();
             wb.flags |= kWcSegBegin;
-            we.flags |= kWcSegEnd;
-            if (sl.flags & kSliceDirect) {
-                we.flags |= kWcDirect;
-                if (S.start[sl.out_set] < 0) {
-                    we.flags |= kWcOutPool;
-                    we.out = S.pool_off[sl.out_set];
-                } else {
-                    we.out = S.start[sl.out_set];
-                }
-            } else {
-                we.out = sl.scratch_off;
-            }
+            we.flags |= kWcSegEnd | out_flags;
+            we.out = out_ref;
             // work items never mix local and remote segments: the local items run while x is gathered
             const bool last_local = !(sl.flags & kSliceRemote) && i + 1 < P.n_fused_slices + P.n_warp_slices &&
                                     (P.slices[i + 1].flags & kSliceRemote);

@@ -43,6 +43,10 @@ constexpr int kWSlots = 16;             // mbarrier slots of one warp: chunks in
 constexpr int kWMaxCols = 64;           // columns per warp-stream chunk (two prefetched x values per lane)
 // bsm_wchunk.flags
 constexpr int kWcT = 1, kWcXPool = 2, kWcOutPool = 4, kWcSegBegin = 8, kWcSegEnd = 16, kWcDirect = 32;
+constexpr int kWcCtaPart = 64;          // the item is one of the kWItemsPerCta parts of a segment: at its end the warp
+                                        // hands its partial vector to the CTA, warp 0 sums the parts in order and writes
+constexpr int kWItemsPerCta = 4;        // == kernels.cuh kWWarps
+constexpr int kWCtaMaxSegments = 592;   // CTA-part mode only when every segment's CTA is resident at once (148 SMs x 4)
 constexpr int kFormT = 1;               // bsm_contrib.form bit0: T-form
 constexpr int kFormFusedT = 2;          // bit1: also emits the transposed partial of the same block
 constexpr int kMaxSliceHeight = 128;   // outputs per work item (one CTA of 128 threads)
@@ -107,6 +111,9 @@ struct HostPlan {
     int64_t n_warp_slices = 0;          // follow the fused slices; the rest go to gather_gemv_kernel
     std::vector<bsm_wchunk> wchunk;     // chunk stream of the warp slices, in slice order
     std::vector<int32_t> witem_ptr;     // warp work items: chunk ranges cut at segment boundaries
+    bool wcta = false;                  // small problems: every segment is ONE CTA of stream_warp_kernel, its chunk list
+                                        // dealt to the kWItemsPerCta warps (items 4c .. 4c+3 = the parts of segment c,
+                                        // possibly empty); single launch, no partial sums through global memory
     // multi-RHS (SpMM) path: usable when every slice is a direct warp-class slice (short segments that
     // own their rows); CTA work items = ranges of those slices, balanced by bytes
     // colour-ordered variant (plans 4/5): slices sorted by (sweep, colour); launch l runs slices
@@ -159,6 +166,7 @@ struct PlanParams {
                                        // this is cut along its block list into several work items (partial sums
                                        // through the gather lists) to expose enough parallelism; 0: off
     int64_t witem_bytes = 0;           // target bytes per warp work item (0: derived from the total)
+    bool wcta = true;                  // small problems with few segments may use the CTA-part mode (HostPlan::wcta)
 };
 
 // Lays the blocks out in the arena (fills block_off, arena_elems, stored).
@@ -181,6 +189,7 @@ struct PeerX {
     int32_t *state = nullptr;
     int32_t rank = 0;
     int32_t debug = 0;
+    long long *dbg = nullptr;
 };
 
 // ---- sparse.cu <-> abi.cu (the handle's internals stay in abi.cu) --------------------------------------

@@ -48,6 +48,11 @@ class Comm:
     def set_debug(self, flags: int):
         L.check(L.lib().bsm_dist_set_debug(self._h, int(flags)))
 
+    def debug_read(self):
+        out = np.zeros(8, np.int64)
+        L.check(L.lib().bsm_dist_debug_read(self._h, out.ctypes.data_as(POINTER(c_int64))))
+        return out
+
     def nccl_version(self) -> int:
         v = c_int(0)
         L.check(L.lib().bsm_dist_info(self._h, None, None, byref(v)))

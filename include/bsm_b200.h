@@ -86,7 +86,8 @@ typedef struct {
     int64_t own_col_lo, own_col_hi;
     int64_t plan_hints;    /* 0 = automatic. Bits, for experiments and comparison runs: 1 = short segments go to the CTA-stream
                               kernel, not the warp-stream kernel; 2 = never cut the segments of a small (L2-resident) problem
-                              into per-block work items (no partial sums, single launch) */
+                              into per-block work items; 4 = small problems keep the round-1 schedule (per-block work items, partial
+                              sums through scratch, gather pass) instead of the single-launch CTA-part mode */
     int64_t reserved[3];
 } bsm_options;
 
@@ -283,8 +284,13 @@ int bsm_dist_set_overlap(bsm_comm c, int on);
  * right-hand side (no staging; 10x slower on 8 GPUs, kept for comparison). */
 int bsm_dist_set_collective(bsm_comm c, int use_broadcasts);
 /* Benchmarking only: bit0 = peer-mode multiplies skip the wait of the entry barrier, bit1 = of the exit barrier
- * (results are then only valid when x does not change between multiplies). */
+ * (results are then only valid when x does not change between multiplies); bit2 = every arrival waits at system
+ * scope; bit3 = the kernels stamp %globaltimer around the barriers; bit4 = relaxed instead of release signals.
+ * bsm_dist_debug_read returns (and resets) the sums over the multiplies since the last read: out[0] ns between a
+ * kernel's first arrival and the end of its entry wait, out[1] ns first arrival -> last arrival, out[2] ns of the
+ * exit wait, out[3] multiplies counted. */
 int bsm_dist_set_debug(bsm_comm c, int flags);
+int bsm_dist_debug_read(bsm_comm c, int64_t out[8]);
 int bsm_dist_info(bsm_comm c, int *nranks, int *rank, int *nccl_version);
 /* In-place all-gather of the row slabs of a column-major (rows x nrhs, leading dimension ldx) DEVICE
  * array: on return every rank holds all rows. cuts has nranks+1 entries (0-based, non-decreasing). */

@@ -65,9 +65,19 @@ def main():
         return [round(float(o.item()), 4) for o in out]
 
     res = {"workload": spec["desc"], "n_gpus": world, "own_rows": list(map(int, SM.own))}
-    for name, flags in (("peer", 0), ("peer_no_entry_wait", 1), ("peer_no_exit_wait", 2), ("peer_no_waits", 3)):
+    for name, flags in (("peer", 0), ("peer_no_entry_wait", 1), ("peer_no_exit_wait", 2), ("peer_no_waits", 3),
+                        ("peer_relaxed_signals", 16), ("peer_every_arrival_waits_sys", 4), ("peer_timed", 8)):
         comm.set_debug(flags)
+        comm.debug_read()
         res[name] = timed(lambda: SM.mul_peer(op, xs, y), args.steps)
+        if flags & 8:
+            t = comm.debug_read()
+            cnt = max(int(t[3]), 1)
+            mine = {"entry_wait_us": t[0] / cnt / 1e3, "first_to_last_arrival_us": t[1] / cnt / 1e3,
+                    "exit_wait_us": t[2] / cnt / 1e3, "multiplies": int(t[3])}
+            allt = [None] * world
+            dist.all_gather_object(allt, mine)
+            res["barrier_timers_per_rank"] = allt
     comm.set_debug(0)
     res["nccl_allgather"] = timed(lambda: SM.mul(op, x_rep, y), args.steps)
     res["local_kernel_only"] = timed(lambda: SM.local.mul(op, x_rep, y), args.steps)

@@ -157,20 +157,32 @@ def run_warp_stream(D, plan, arena, S, slices, x_full, x_local, y, scratch, writ
     if not wsl:
         assert chunks.size == 0 and iptr.size == 0
         return
-    assert iptr[0] == 0 and iptr[-1] == len(chunks) and np.all(np.diff(iptr) > 0)
+    cta_mode = bool(np.any(chunks["flags"] & 64))
+    assert iptr[0] == 0 and iptr[-1] == len(chunks)
+    if cta_mode:
+        # CTA-part mode: items 4c .. 4c+3 are the parts of segment c (part 0 never empty, later parts may be); every
+        # part ends with a CtaPart record carrying the SAME output reference; the CTA sums the parts in order
+        assert (len(iptr) - 1) == 4 * len(wsl) and np.all(np.diff(iptr) >= 0) and np.all(np.diff(iptr)[0::4] > 0)
+        assert np.all((chunks["flags"][(chunks["flags"] & 16) != 0] & 64) != 0), "every segment end must be a part end"
+    else:
+        assert np.all(np.diff(iptr) > 0)
     raw = arena.view(np.uint8)
     isz = arena.dtype.itemsize
     nseg = 0
     seg = 0
+    part_acc, part_info = None, None
     for it in range(len(iptr) - 1):
         acc = None
         check_ring_schedule(chunks[iptr[it]:iptr[it + 1]], isz)
         # a work item is all-local or all-remote (local items run while x is being gathered)
-        nseg_item = int(np.sum((chunks[iptr[it]:iptr[it + 1]]["flags"] & 16) != 0))
-        kinds = {bool(wsl[seg + k]["flags"] & 16) for k in range(nseg_item)}
-        assert len(kinds) == 1, "a warp work item mixes local and remote segments"
-        x = x_full if kinds.pop() else x_local
-        seg += nseg_item
+        if cta_mode:
+            x = x_full if (wsl[it // 4]["flags"] & 16) else x_local
+        else:
+            nseg_item = int(np.sum((chunks[iptr[it]:iptr[it + 1]]["flags"] & 16) != 0))
+            kinds = {bool(wsl[seg + k]["flags"] & 16) for k in range(nseg_item)}
+            assert len(kinds) == 1, "a warp work item mixes local and remote segments"
+            x = x_full if kinds.pop() else x_local
+            seg += nseg_item
         for q in range(iptr[it], iptr[it + 1]):
             c = chunks[q]
             fl, m, nc, Lseg = int(c["flags"]), int(c["m"]), int(c["ncols"]), int(c["seg_len"])
@@ -194,7 +206,17 @@ def run_warp_stream(D, plan, arena, S, slices, x_full, x_local, y, scratch, writ
                 acc[oc:oc + nc] += Bc.T @ xi
             else:
                 acc[:m] += Bc @ xi
-            if fl & 16:
+            if (fl & 16) and (fl & 64):
+                info = (fl & (4 | 32), int(c["out"]), Lseg)
+                assert q == iptr[it + 1] - 1, "a part holds exactly one (partial) segment"
+                if part_acc is None:
+                    assert it % 4 == 0
+                    part_acc, part_info = acc.copy(), info
+                else:
+                    assert info == part_info, "the parts of a segment must agree on its output"
+                    part_acc += acc
+                acc = None
+            elif fl & 16:
                 o = int(c["out"])
                 if fl & 32:
                     rows = S.pool[o:o + Lseg].astype(np.int64) if (fl & 4) else np.arange(o, o + Lseg)
@@ -207,6 +229,18 @@ def run_warp_stream(D, plan, arena, S, slices, x_full, x_local, y, scratch, writ
                 acc = None
                 nseg += 1
         assert acc is None, "work item must end at a segment boundary"
+        if cta_mode and it % 4 == 3:          # the CTA's single write
+            pfl, o, Lseg = part_info
+            if pfl & 32:
+                rows = S.pool[o:o + Lseg].astype(np.int64) if (pfl & 4) else np.arange(o, o + Lseg)
+                assert np.all(written[rows] == 0), "direct rows written twice"
+                written[rows] += 1
+                y[rows] = alpha * part_acc + (0 if beta_false else beta * y[rows])
+            else:
+                assert np.all(np.isnan(scratch[o:o + Lseg]))
+                scratch[o:o + Lseg] = part_acc
+            part_acc, part_info = None, None
+            nseg += 1
     assert nseg == len(wsl)
     for s in wsl:
         assert s["r0"] == 0 and s["r1"] == S.len[s["out_set"]] <= 64

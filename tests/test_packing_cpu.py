@@ -413,3 +413,31 @@ def test_random_symmetric_structures(seed):
             S = extract_slab(A, lo, hi, ("N",))
             run_plan(S, host_only(S, own_rows=(lo, hi), own_cols=(lo, hi)), "N", x, y=y, own=(lo, hi), in_own=(lo, hi))
         assert rel(y, O.mul_sbm(OA, x, "N")) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32])
+def test_small_problem_cta_part_mode_is_single_launch(dtype):
+    """C1 shape (BASELINE configs[0]): 312 block rows of ~6 blocks each. Small problems with few segments run as ONE
+    launch: every segment is a CTA of the warp-stream kernel, its chunk list dealt to the four warps (CtaPart records),
+    the rows no block touches are set by extra CTAs of the same launch — no partial sums through scratch."""
+    from bsm_b200 import generators as G
+    from helpers import oracle_mul
+    A = G.blocksparse_uniform(seed=1, dtype=dtype)
+    D = host_only(A)
+    rng = np.random.default_rng(2)
+    for op, plan in (("N", 2), ("T", 3)):
+        ch = D.table(L.TAB_WCHUNK, plan)
+        iptr = D.table(L.TAB_WITEM_PTR, plan)
+        sl = D.table(L.TAB_SLICE, plan)
+        assert np.any(ch["flags"] & 64) and len(iptr) - 1 == 4 * len(sl)
+        assert np.all(sl["flags"] & 1), "every block row owns its rows"
+        assert D.plan_stats(op)["scratch_elems"] == 0 and D.launch_count(op) == 1
+        x = rng.standard_normal(A.size[1]).astype(dtype)
+        y0 = rng.standard_normal(A.size[0]).astype(dtype)
+        tol = 1e-5 if dtype == np.float32 else 1e-13
+        assert rel(run_plan(A, D, op, x, variant="fused"), oracle_mul(A, x, op, f64=(dtype == np.float32))) < tol
+        assert rel(run_plan(A, D, op, x, 0.7, -0.4, False, y0.copy(), variant="fused"),
+                   oracle_mul(A, x, op, 0.7, -0.4, False, y0.copy(), f64=(dtype == np.float32))) < tol
+    # the explicit hint restores per-block work items + gather pass (comparison)
+    D2 = host_only(A, plan_hints=4)
+    assert not np.any(D2.table(L.TAB_WCHUNK, 2)["flags"] & 64) and D2.launch_count("N") == 2
