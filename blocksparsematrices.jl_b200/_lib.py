@@ -25,7 +25,7 @@ class Options(ctypes.Structure):
     _fields_ = [("device", c_int32), ("variant", c_int32),
                 ("own_row_lo", c_int64), ("own_row_hi", c_int64),
                 ("own_col_lo", c_int64), ("own_col_hi", c_int64),
-                ("plan_hints", c_int64), ("reserved", c_int64 * 3)]
+                ("plan_hints", c_int64), ("blocks_on_device", c_int64), ("reserved", c_int64 * 2)]
 
 
 class CgOptions(ctypes.Structure):
@@ -51,6 +51,8 @@ SIGNATURES = [
                                  POINTER(c_void_p), _P64, _P64, POINTER(c_uint8), POINTER(Options),
                                  POINTER(c_void_p)]),
     ("bsm_update_values", c_int, [c_void_p, POINTER(c_void_p), c_int64]),
+    ("bsm_update_values_dev", c_int, [c_void_p, POINTER(c_void_p), c_int64]),
+    ("bsm_vbcrs_sort_dev", c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, _P64, c_void_p]),
     ("bsm_destroy", c_int, [c_void_p]),
     ("bsm_mul", c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64,
                         c_int64, c_void_p]),

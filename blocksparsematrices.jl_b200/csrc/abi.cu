@@ -105,6 +105,7 @@ struct bsm_matrix {
     // sparse(A) result built by bsm_sparse_build (sparse.cu), device arrays
     void *sparse_slot[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool restricted = false;
+    bool blocks_on_device = false;  // the block sources of the pending upload are device pointers
     // tensor maps of the arena for spmm_tma_kernel (encoded on the first multi-RHS multiply)
     TmaMaps tma_maps;
     bool tma_maps_ready = false;
@@ -155,7 +156,13 @@ int resolve_device(const bsm_options *opt, int *dev) {
     return 0;
 }
 
-// Copies every block into the device arena through two pinned staging buffers.
+}  // namespace
+int bsm_arena_gather_dev(void *arena, int esize, const std::vector<bsm::BlockSrc> &blocks, const std::vector<int64_t> &off,
+                         cudaStream_t st);   // construct.cu
+namespace {
+
+// Copies every block into the device arena through two pinned staging buffers (host blocks), or gathers them in HBM
+// (device blocks).
 int upload_arena(bsm_matrix *A) {
     HostMatrix &H = A->H;
     const int64_t s = dtype_size(H.dtype);
@@ -163,6 +170,7 @@ int upload_arena(bsm_matrix *A) {
         CUDA_TRY(cudaMalloc(&A->arena, (size_t)H.arena_elems * s));
         CUDA_TRY(cudaMemset(A->arena, 0, (size_t)H.arena_elems * s));
     }
+    if (A->blocks_on_device) return bsm_arena_gather_dev(A->arena, (int)s, H.blocks, H.block_off, nullptr);
     const int64_t stage_bytes = 64ll << 20;
     unsigned char *stage[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
@@ -334,6 +342,7 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
         pp[1].in_hi = opt->own_row_hi;
         A->variant = opt->variant;
         A->restricted = opt->own_row_hi >= 0 || opt->own_col_hi >= 0;
+        A->blocks_on_device = opt->blocks_on_device != 0;
     }
     // work-item budget of the stream plans: no CTA should hold more than ~1/8 of a resident slot's fair share (LPT tail <= ~6 %)
     const int64_t total_bytes = [&] {
@@ -386,6 +395,7 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
         return rc;
     }
     for (auto &b : H.blocks) b.host = nullptr;  // host blocks are not referenced after create
+    A->blocks_on_device = false;
     *out = A;
     return 0;
 }
@@ -1092,6 +1102,14 @@ int bsm_update_values(bsm_handle h, const void *const *blocks, int64_t nb) {
     CUDA_TRY(cudaDeviceSynchronize());   // no multiply may still be reading the arena
     const int rc = upload_arena(h);
     for (auto &b : h->H.blocks) b.host = nullptr;
+    return rc;
+}
+
+int bsm_update_values_dev(bsm_handle h, const void *const *dev_blocks, int64_t nb) {
+    if (int rc = check_handle(h)) return rc;
+    h->blocks_on_device = true;
+    const int rc = bsm_update_values(h, dev_blocks, nb);
+    h->blocks_on_device = false;
     return rc;
 }
 

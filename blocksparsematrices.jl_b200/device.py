@@ -36,6 +36,27 @@ def _pool(vecs):
     return np.ascontiguousarray(pool, dtype=np.int64), ptr
 
 
+def _device_blocks(tensors, shapes, dt, allow_transposed=False):
+    """Device pointers of torch CUDA blocks (column-major: stride (1, m); or, where allowed, C-contiguous = the
+    parent of a lazy transpose). Returns (pointer array, transposed flags)."""
+    tdt = _torch_dtype(dt)
+    ptrs = np.zeros(max(len(tensors), 1), np.uintp)
+    tr = np.zeros(len(tensors), np.uint8)
+    if len(tensors) != len(shapes):
+        raise ValueError("device_blocks must list one tensor per block, in creation order")
+    for i, (t, (m, n)) in enumerate(zip(tensors, shapes)):
+        if not t.is_cuda or t.dtype != tdt or tuple(t.shape) != (m, n):
+            raise TypeError(f"device block {i}: expected a CUDA tensor of shape {(m, n)} and dtype {tdt}")
+        if m * n == 0 or (t.stride(0) == 1 and (n <= 1 or t.stride(1) == m)):
+            pass
+        elif allow_transposed and t.is_contiguous():
+            tr[i] = 1
+        else:
+            raise ValueError(f"device block {i} must be column-major (stride (1, rows))")
+        ptrs[i] = t.data_ptr()
+    return ptrs, tr
+
+
 def _colmajor(blocks, dt, allow_transposed=False):
     """Column-major views of the blocks (copies only where the memory is not already column-major of
     the right dtype). Returns (keepalive list, pointer array, m, n, transposed flags)."""
@@ -64,7 +85,10 @@ class DeviceMatrix:
     """Opaque handle + size: what `B200(A)` of the Julia extension returns."""
 
     def __init__(self, A: AbstractBlockMatrix, device: int = -1, variant: int = L.VARIANT_AUTO,
-                 own_rows=None, own_cols=None, plan_hints: int = 0):
+                 own_rows=None, own_cols=None, plan_hints: int = 0, device_blocks=None):
+        """device_blocks: optional list of torch CUDA tensors holding the block VALUES in HBM (creation order;
+        symmetric: the diagonal blocks, then the off-diagonal blocks). The arena is then filled by a gather kernel on
+        the device — nothing crosses PCIe; A only supplies the structure (its host blocks are not read)."""
         lib = L.lib()
         self.host = A
         self.size = A.size
@@ -77,14 +101,18 @@ class DeviceMatrix:
         opt.device = device
         opt.variant = variant
         opt.plan_hints = plan_hints
+        opt.blocks_on_device = 1 if device_blocks is not None else 0
         if own_rows is not None:
             opt.own_row_lo, opt.own_row_hi = int(own_rows[0]), int(own_rows[1])
         if own_cols is not None:
             opt.own_col_lo, opt.own_col_hi = int(own_cols[0]), int(own_cols[1])
         h = c_void_p()
         vp = lambda a: a.ctypes.data_as(POINTER(c_void_p))
+        shp = lambda bs: [tuple(np.shape(b)) for b in bs]
         if isinstance(A, BlockSparseMatrix):
             keep, ptrs, m, n, _ = _colmajor(A.blocks, self.dtype)
+            if device_blocks is not None:
+                ptrs, _ = _device_blocks(device_blocks, shp(A.blocks), self.dtype)
             rp, rptr = _pool(A.rowindices)
             cp, cptr = _pool(A.colindices)
             L.check(lib.bsm_create_blocksparse(dt, A.size[0], A.size[1], len(A.blocks), vp(ptrs), _i64p(m),
@@ -95,6 +123,10 @@ class DeviceMatrix:
             if np.any(dm != dn):
                 raise ValueError("diagonal blocks must be square")
             keepo, optrs, om, on, _ = _colmajor(A.offdiagonals, self.dtype)
+            if device_blocks is not None:
+                nd = len(A.diagonals)
+                dptrs, _ = _device_blocks(device_blocks[:nd], shp(A.diagonals), self.dtype)
+                optrs, _ = _device_blocks(device_blocks[nd:], shp(A.offdiagonals), self.dtype)
             dp, dptr = _pool(A.diagonalindices)
             rp, rptr = _pool(A.rowindices)
             cp, cptr = _pool(A.colindices)
@@ -104,6 +136,8 @@ class DeviceMatrix:
                                              _i64p(cptr), byref(opt), byref(h)))
         elif isinstance(A, VariableBlockCompressedRowStorage):
             keep, ptrs, m, n, tr = _colmajor(A.blocks, self.dtype, allow_transposed=True)
+            if device_blocks is not None:
+                ptrs, tr = _device_blocks(device_blocks, shp(A.blocks), self.dtype, allow_transposed=True)
             rowptr = np.ascontiguousarray(A.rowptr, np.int64)
             cs = np.ascontiguousarray(A.colindices, np.int64)
             rs = np.ascontiguousarray(A.rowindices, np.int64)
@@ -141,6 +175,18 @@ class DeviceMatrix:
         keep, ptrs, m, n, tr = _colmajor(blocks, self.dtype, allow_transposed=allow_tr)
         L.check(L.lib().bsm_update_values(self._h, ptrs.ctypes.data_as(POINTER(c_void_p)), len(blocks)))
         self.host = A
+
+    def update_values_dev(self, device_blocks):
+        """New values from blocks that live in HBM (torch CUDA tensors, creation order): bsm_update_values_dev."""
+        A = self.host
+        if isinstance(A, SymmetricBlockMatrix):
+            shapes = [tuple(np.shape(b)) for b in list(A.diagonals) + list(A.offdiagonals)]
+            allow_tr = False
+        else:
+            shapes = [tuple(np.shape(b)) for b in A.blocks]
+            allow_tr = isinstance(A, VariableBlockCompressedRowStorage)
+        ptrs, _ = _device_blocks(device_blocks, shapes, self.dtype, allow_transposed=allow_tr)
+        L.check(L.lib().bsm_update_values_dev(self._h, ptrs.ctypes.data_as(POINTER(c_void_p)), len(shapes)))
 
     # ---- lifetime
     def close(self):
@@ -372,3 +418,25 @@ class DeviceAdjoint(_Wrapped):
 
 class DeviceTranspose(_Wrapped):
     _op = "T"
+
+
+def vbcrs_sort_device(rowstart, colstart):
+    """The VBCRS sorting constructor on the device (bsm_vbcrs_sort_dev, src/vbcrs.jl:78-122): rowstart / colstart are
+    1-based int64 CUDA tensors (one entry per block, unsorted). Returns (perm, rowptr, rowindices, colindices) as CUDA
+    tensors: perm[k] = 0-based input index of the block that becomes block k (stable), rowptr 1-based with sentinel."""
+    import torch
+    nb = int(rowstart.numel())
+    if rowstart.dtype != torch.int64 or colstart.dtype != torch.int64 or not rowstart.is_cuda or colstart.numel() != nb:
+        raise TypeError("rowstart / colstart must be int64 CUDA tensors of equal length")
+    dev = rowstart.device
+    perm = torch.empty(nb, dtype=torch.int64, device=dev)
+    rowptr = torch.empty(nb + 1, dtype=torch.int64, device=dev)
+    rowidx = torch.empty(max(nb, 1), dtype=torch.int64, device=dev)
+    colidx = torch.empty(max(nb, 1), dtype=torch.int64, device=dev)
+    nbrows = c_int64(0)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    L.check(L.lib().bsm_vbcrs_sort_dev(nb, c_void_p(rowstart.contiguous().data_ptr()), c_void_p(colstart.contiguous().data_ptr()),
+                                       c_void_p(perm.data_ptr()), c_void_p(rowptr.data_ptr()), c_void_p(rowidx.data_ptr()),
+                                       c_void_p(colidx.data_ptr()), byref(nbrows), c_void_p(st)))
+    nr = int(nbrows.value)
+    return perm, rowptr[:nr + 1], rowidx[:nr], colidx[:nb]

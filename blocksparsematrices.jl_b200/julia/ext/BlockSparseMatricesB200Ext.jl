@@ -28,9 +28,10 @@ struct BsmOptions                     # mirrors bsm_options
     own_col_lo::Int64
     own_col_hi::Int64
     plan_hints::Int64
-    reserved::NTuple{3,Int64}
+    blocks_on_device::Int64
+    reserved::NTuple{2,Int64}
 end
-BsmOptions(; device=-1, variant=0) = BsmOptions(device, variant, 0, -1, 0, -1, 0, (0, 0, 0))
+BsmOptions(; device=-1, variant=0) = BsmOptions(device, variant, 0, -1, 0, -1, 0, 0, (0, 0))
 
 check(rc) = rc == 0 || error("libbsm_b200: " * unsafe_string(ccall((:bsm_last_error, libbsm_b200), Cstring, ())))
 

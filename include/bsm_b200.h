@@ -88,7 +88,9 @@ typedef struct {
                               kernel, not the warp-stream kernel; 2 = never cut the segments of a small (L2-resident) problem
                               into per-block work items; 4 = small problems keep the round-1 schedule (per-block work items, partial
                               sums through scratch, gather pass) instead of the single-launch CTA-part mode */
-    int64_t reserved[3];
+    int64_t blocks_on_device; /* != 0: the block pointers handed to bsm_create_* are DEVICE pointers (blocks assembled on the
+                              GPU): the arena is filled by a gather kernel in HBM, nothing crosses PCIe */
+    int64_t reserved[2];
 } bsm_options;
 
 void bsm_default_options(bsm_options *opt);
@@ -126,6 +128,17 @@ int bsm_create_vbcrs(int dtype, int64_t nrows, int64_t ncols, int64_t nbrows, in
  * (symmetric: the diagonal blocks, then the off-diagonal blocks), each of the shape (and, for VBCRS, the
  * is_transposed flag) given at creation. Synchronises the device first. */
 int bsm_update_values(bsm_handle h, const void *const *blocks, int64_t nb);
+/* The same with DEVICE block pointers (a host array of nb device pointers): gathered into the arena in HBM. */
+int bsm_update_values_dev(bsm_handle h, const void *const *dev_blocks, int64_t nb);
+
+/* The sorting constructor of VariableBlockCompressedRowStorage on the device (src/vbcrs.jl:78-122): from the unsorted
+ * block list (1-based Int64 row start and column start per block, DEVICE arrays of nb entries) computes the STABLE
+ * sort permutation by (row start, column start) — perm[k] = 0-based input index of the block that becomes block k —,
+ * the block-row pointer (1-based, nbrows+1 entries used, sentinel nb+1), the start row of every block row and the
+ * sorted column starts; all outputs are DEVICE arrays of nb (+1) entries. Bit-identical to the host constructor. */
+int bsm_vbcrs_sort_dev(int64_t nb, const int64_t *rowstart_dev, const int64_t *colstart_dev, int64_t *perm_dev,
+                       int64_t *rowptr_dev, int64_t *rowindices_dev, int64_t *colindices_dev, int64_t *nbrows_out,
+                       void *stream);
 
 int bsm_destroy(bsm_handle h);
 

@@ -505,3 +505,75 @@ def test_cg_through_the_operator(dtype, hermitian):
     assert np.linalg.norm(res) / np.linalg.norm(b) < (5e-4 if dtype == np.float32 else 5e-10)
     x2, it2, rel2_ = D.cg(torch.from_numpy(b).cuda(), rtol=rtol, maxit=100, hermitian=hermitian)
     assert it2 == it and torch.equal(x, x2)
+
+
+# ---- device-side construction ------------------------------------------------------------------
+def _to_cuda_colmajor(blocks, torch):
+    out = []
+    for b in blocks:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(b).T)).cuda().t()      # column-major on the device
+        out.append(t)
+    return out
+
+
+@pytest.mark.parametrize("kind", ["bsm", "sbm", "vbcrs"])
+def test_blocks_already_in_hbm_build_the_same_arena(kind):
+    """bsm_options.blocks_on_device: the arena gathered in HBM from device-resident blocks is bit-identical to the one
+    uploaded from host blocks, every table is the same, and the products agree bitwise; bsm_update_values_dev swaps in
+    new values without re-planning."""
+    import torch
+    if kind == "bsm":
+        A = G.blocksparse_uniform(seed=71, n=3200, nblocks=400, bs=32, dtype=np.complex128, permuted=True)
+        blocks = A.blocks
+    elif kind == "sbm":
+        A = G.symmetric_nearfield(seed=72, n=8000, k_near=3)
+        blocks = list(A.diagonals) + list(A.offdiagonals)
+    else:
+        A = G.vbcrs_variable(seed=73, n=9000, dtype=np.float32)
+        blocks = A.blocks
+    Dh = B.DeviceMatrix(A)
+    dev_blocks = _to_cuda_colmajor(blocks, torch)
+    Dd = B.DeviceMatrix(A, device_blocks=dev_blocks)
+    for tab in (L.TAB_ARENA, L.TAB_BLOCK_OFF, L.TAB_POOL):
+        assert np.array_equal(Dh.table(tab).view(np.uint8), Dd.table(tab).view(np.uint8)), tab
+    for plan in (2, 3):
+        for tab in (L.TAB_CONTRIB, L.TAB_SLICE, L.TAB_WCHUNK):
+            assert np.array_equal(Dh.table(tab, plan), Dd.table(tab, plan))
+    rng = np.random.default_rng(4)
+    x = randx(rng, A.size[1], A.dtype)
+    assert np.array_equal(Dh.mul("N", x), Dd.mul("N", x))
+    # new values, same structure, straight from HBM
+    scaled = [2 * t for t in dev_blocks]
+    Dd.update_values_dev(scaled)
+    y2 = Dd.mul("N", x)
+    assert rel2(y2, 2 * oracle_mul(A, x, "N", f64=(np.dtype(A.dtype) == np.float32))) < TOL[np.dtype(A.dtype)]
+
+
+def test_vbcrs_sorting_constructor_on_the_device():
+    """bsm_vbcrs_sort_dev against the host constructor (host.py, stable lexsort = sortperm of src/vbcrs.jl:84): the
+    permutation, rowptr, rowindices and colindices must be bit-identical, duplicates of (row start, column start)
+    included (stability)."""
+    import torch
+    from bsm_b200.device import vbcrs_sort_device
+    rng = np.random.default_rng(5)
+    for nb, nrow, ncol in ((1, 1, 1), (50, 7, 9), (20000, 3000, 2500), (100000, 100000, 100000)):
+        rs = rng.integers(1, nrow + 1, nb).astype(np.int64)
+        cs = rng.integers(1, ncol + 1, nb).astype(np.int64)
+        perm, rowptr, rowidx, colidx = vbcrs_sort_device(torch.from_numpy(rs).cuda(), torch.from_numpy(cs).cuda())
+        href = np.lexsort((cs, rs))                       # stable, keyed by (row start, column start)
+        assert np.array_equal(perm.cpu().numpy(), href)
+        srs, scs = rs[href], cs[href]
+        heads = np.flatnonzero(np.r_[True, srs[1:] != srs[:-1]])
+        assert np.array_equal(rowptr.cpu().numpy(), np.r_[heads + 1, nb + 1])
+        assert np.array_equal(rowidx.cpu().numpy(), srs[heads])
+        assert np.array_equal(colidx.cpu().numpy(), scs)
+    # the same through the host-side constructor of the mirror (what the reference's struct holds)
+    V = G.vbcrs_variable(seed=74, n=20000)
+    # the generator hands the blocks over unsorted; the mirror sorted them: recover the unsorted starts from its fields
+    rs_sorted = np.repeat(V.rowindices, np.diff(V.rowptr))
+    shuffle = rng.permutation(len(V.blocks))
+    perm, rowptr, rowidx, colidx = vbcrs_sort_device(torch.from_numpy(rs_sorted[shuffle]).cuda(),
+                                                     torch.from_numpy(np.asarray(V.colindices)[shuffle]).cuda())
+    assert np.array_equal(rowptr.cpu().numpy(), V.rowptr) and np.array_equal(rowidx.cpu().numpy(), V.rowindices)
+    assert np.array_equal(colidx.cpu().numpy(), V.colindices)
+    assert np.array_equal(shuffle[perm.cpu().numpy()], np.arange(len(V.blocks)))
