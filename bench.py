@@ -304,6 +304,9 @@ def run_workload(cx, name, primary):
     hard = args.hard if name == "c2" else ""
     spec = workload_spec(name, args.scale, hard)
     op = args.op or spec["op"]
+    if args.nrhs and "nrhs" in spec:
+        spec["nrhs"] = args.nrhs
+        spec["desc"] = spec["desc"].replace("64 right-hand sides", f"{args.nrhs} right-hand sides")
     nrhs = spec.get("nrhs", 1)
     npdt = np.dtype(NPDT[spec["dtype"]])
     tdt = {"c128": torch.complex128, "f64": torch.float64, "f32": torch.float32}[spec["dtype"]]
@@ -595,6 +598,7 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-gather, then multiply, on one stream")
     ap.add_argument("--op", default=None, choices=["N", "T", "C"], help="override the workload's op (development)")
     ap.add_argument("--plan-hints", type=int, default=0, help="bsm_options.plan_hints (development)")
+    ap.add_argument("--nrhs", type=int, default=0, help="c5: number of right-hand sides (development; default 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="default workload only: skip the c3 / c5 companion results")
     args = ap.parse_args()

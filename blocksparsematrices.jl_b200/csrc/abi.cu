@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -350,7 +351,11 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
         for (const auto &b : H.blocks) t += (int64_t)b.m * b.n * dtype_size(H.dtype);
         return t;
     }();
-    const int64_t split = std::max<int64_t>(256 << 10, total_bytes / (148 * 2 * 8));
+    // BSM_TUNE_SPLIT_DIV / BSM_TUNE_WITEMS_PER_SLOT: development knobs for the work-item granularity (profiles/tools)
+    const char *tune_split = std::getenv("BSM_TUNE_SPLIT_DIV"), *tune_witems = std::getenv("BSM_TUNE_WITEMS_PER_SLOT");
+    const int64_t split_div = tune_split ? std::max(1, std::atoi(tune_split)) : 8;
+    const int64_t split = std::max<int64_t>(256 << 10, total_bytes / (148 * 2 * split_div));
+    if (tune_witems) pp[0].witems_per_slot = pp[1].witems_per_slot = std::max(1, std::atoi(tune_witems));
     std::string err = build_plan(H, ir[0], H.nrows, H.ncols, pp[0], H.plan[0]);
     if (err.empty()) err = build_plan(H, ir[1], H.ncols, H.nrows, pp[1], H.plan[1]);
     if (H.has_fused) {

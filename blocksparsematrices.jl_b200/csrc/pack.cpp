@@ -505,7 +505,14 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
             for (int32_t c = P.slices[i].c_begin; c < P.slices[i].c_end; ++c)
                 total += (int64_t)P.contrib[c].m * P.contrib[c].n * s;
         int64_t target = pp.witem_bytes;
-        if (target <= 0) target = std::min<int64_t>(1 << 20, std::max<int64_t>(4 << 10, total / (148 * 8 * 6)));
+        // items per warp slot (148 SMs x 16 resident warps): three for large problems (tail of the last wave), ONE when a
+        // slot streams less than ~100 KB in total — every item start costs a ~3 us pipeline bubble (item pointer ->
+        // descriptors -> first chunk), which a 34 KB item (5 us of streaming) cannot amortise (measured on the 240 MB
+        // slabs of C3 on 8 GPUs: 60 us against 37 us at the roofline)
+        if (target <= 0) {
+            const int64_t per_slot = pp.witems_per_slot > 0 ? pp.witems_per_slot : (total < ((int64_t)768 << 20) ? 1 : 3);
+            target = std::min<int64_t>(1 << 20, std::max<int64_t>(4 << 10, total / (148 * 16 * per_slot) + 1));
+        }
         P.witem_ptr.push_back(0);
         int64_t item_bytes = 0;
         for (int64_t i = P.n_fused_slices; i < P.n_fused_slices + P.n_warp_slices; ++i) {

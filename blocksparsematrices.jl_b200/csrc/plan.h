@@ -166,6 +166,7 @@ struct PlanParams {
                                        // this is cut along its block list into several work items (partial sums
                                        // through the gather lists) to expose enough parallelism; 0: off
     int64_t witem_bytes = 0;           // target bytes per warp work item (0: derived from the total)
+    int64_t witems_per_slot = 0;       // warp work items per resident warp slot (0: automatic)
     bool wcta = true;                  // small problems with few segments may use the CTA-part mode (HostPlan::wcta)
 };
 

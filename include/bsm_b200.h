@@ -298,7 +298,7 @@ int bsm_dist_set_overlap(bsm_comm c, int on);
 int bsm_dist_set_collective(bsm_comm c, int use_broadcasts);
 /* Benchmarking only: bit0 = peer-mode multiplies skip the wait of the entry barrier, bit1 = of the exit barrier
  * (results are then only valid when x does not change between multiplies); bit2 = every arrival waits at system
- * scope; bit3 = the kernels stamp %globaltimer around the barriers; bit4 = relaxed instead of release signals.
+ * scope; bit3 = the kernels stamp %globaltimer around the barriers; bit4 = release instead of relaxed signal stores.
  * bsm_dist_debug_read returns (and resets) the sums over the multiplies since the last read: out[0] ns between a
  * kernel's first arrival and the end of its entry wait, out[1] ns first arrival -> last arrival, out[2] ns of the
  * exit wait, out[3] multiplies counted. */

@@ -66,7 +66,7 @@ def main():
 
     res = {"workload": spec["desc"], "n_gpus": world, "own_rows": list(map(int, SM.own))}
     for name, flags in (("peer", 0), ("peer_no_entry_wait", 1), ("peer_no_exit_wait", 2), ("peer_no_waits", 3),
-                        ("peer_relaxed_signals", 16), ("peer_every_arrival_waits_sys", 4), ("peer_timed", 8)):
+                        ("peer_release_signals", 16), ("peer_every_arrival_waits_sys", 4), ("peer_timed", 8)):
         comm.set_debug(flags)
         comm.debug_read()
         res[name] = timed(lambda: SM.mul_peer(op, xs, y), args.steps)
