@@ -448,7 +448,11 @@ int ensure_attrs(int device) {
                                   (int)fused_tma_smem_bytes<T>()));
     CUDA_TRY(cudaFuncSetAttribute(sym_fused_tma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fused_tma_smem_bytes<T>()));
-    CUDA_TRY(cudaFuncSetAttribute(stream_warp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(stream_warp_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)stream_warp_smem_bytes<T>()));
+    CUDA_TRY(cudaFuncSetAttribute(stream_warp_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)stream_warp_smem_bytes<T>()));
+    CUDA_TRY(cudaFuncSetAttribute(stream_warp_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)stream_warp_smem_bytes<T>()));
     if constexpr (sizeof(T) == 8)
         CUDA_TRY(cudaFuncSetAttribute(spmm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -813,8 +817,13 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
                 w.x.sync.arrivals = (int32_t)((w.nitems + kWWarps - 1) / kWWarps) * kWWarps;
             }
             const unsigned zctas = (unsigned)((w.nz + kWWarps * 32 - 1) / (kWWarps * 32));
-            stream_warp_kernel<T><<<(unsigned)((w.nitems + kWWarps - 1) / kWWarps) + zctas, kWWarps * 32,
-                                    stream_warp_smem_bytes<T>(), st>>>(w);
+            const unsigned wgrid = (unsigned)((w.nitems + kWWarps - 1) / kWWarps) + zctas;
+            if (HP.wform == 0)
+                stream_warp_kernel<T, 0><<<wgrid, kWWarps * 32, stream_warp_smem_bytes<T>(), st>>>(w);
+            else if (HP.wform == 1)
+                stream_warp_kernel<T, 1><<<wgrid, kWWarps * 32, stream_warp_smem_bytes<T>(), st>>>(w);
+            else
+                stream_warp_kernel<T, 2><<<wgrid, kWWarps * 32, stream_warp_smem_bytes<T>(), st>>>(w);
             CUDA_TRY(cudaGetLastError());
         }
         if (g1 > g0) {

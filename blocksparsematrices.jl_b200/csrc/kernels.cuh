@@ -1099,7 +1099,9 @@ __device__ __forceinline__ void wchunk_compute(const T *__restrict__ sm, const T
     }
 }
 
-template <class T, bool CONJ>
+// FORM: 0 = the launch holds N-form chunks only, 1 = T-form only, 2 = both (the dead path is compiled out: half the
+// code, which matters for small problems whose first wave also pays the instruction fetch)
+template <class T, bool CONJ, int FORM>
 __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned char *ring, const int4 *dring,
                                                  T *xs, T *ts, uint64_t *full, uint64_t *dbar, int32_t q0,
                                                  int32_t n, T *cta_part, uint32_t &end_fl, int64_t &end_out, int32_t &end_L) {
@@ -1169,7 +1171,7 @@ __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned 
         const WDesc d0 = desc_at(ci);
         const uint32_t fl = d0.flags();
         const int32_t m = d0.m(), nc = d0.ncols();
-        const bool tform = (fl & 1u) != 0;
+        const bool tform = FORM == 2 ? (fl & 1u) != 0 : FORM == 1;
         const unsigned char *cbase = ring + d0.smem_off();
         const T *xin = reinterpret_cast<const T *>(cbase + d0.bytes());
         if (fl & 8u) {  // first chunk of a segment
@@ -1242,7 +1244,7 @@ constexpr size_t stream_warp_smem_bytes() {
     return kWWarps * stream_warp_smem_per_warp<T>() + kWWarps * kWSegMax * sizeof(T) + 16;   // + the parts of CTA-part mode
 }
 
-template <class T>
+template <class T, int FORM>
 __global__ void __launch_bounds__(kWWarps * 32) stream_warp_kernel(const WarpArgs<T> a) {
     extern __shared__ __align__(128) unsigned char wsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1283,12 +1285,17 @@ __global__ void __launch_bounds__(kWWarps * 32) stream_warp_kernel(const WarpArg
         const int32_t q0 = __ldg(a.item_ptr + item), q1 = __ldg(a.item_ptr + item + 1);
         if (q0 < q1) {
             has_work = true;
-            if (a.conj)
-                stream_warp_body<T, true>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0, parts + warp * kWSegMax, end_fl,
-                                          end_out, end_L);
-            else
-                stream_warp_body<T, false>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0, parts + warp * kWSegMax, end_fl,
-                                           end_out, end_L);
+            bool conj_done = false;
+            if constexpr (sizeof(T) == 16) {       // conj is the identity for real element types: one instantiation
+                if (a.conj) {
+                    stream_warp_body<T, true, FORM>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0, parts + warp * kWSegMax,
+                                                    end_fl, end_out, end_L);
+                    conj_done = true;
+                }
+            }
+            if (!conj_done)
+                stream_warp_body<T, false, FORM>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0, parts + warp * kWSegMax,
+                                                 end_fl, end_out, end_L);
         }
     }
     if (a.cta_mode) {

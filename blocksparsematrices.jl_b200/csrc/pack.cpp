@@ -617,6 +617,11 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
         if (P.witem_ptr.back() != (int32_t)P.wchunk.size()) P.witem_ptr.push_back((int32_t)P.wchunk.size());
         if (!(P.slices[P.n_fused_slices + P.n_warp_slices - 1].flags & kSliceRemote))
             P.n_warp_items_local = (int64_t)P.witem_ptr.size() - 1;   // no remote warp segment at all
+        {
+            bool any_n = false, any_t = false;
+            for (const bsm_wchunk &w : P.wchunk) ((w.flags & kWcT) ? any_t : any_n) = true;
+            P.wform = (any_n && any_t) ? 2 : any_t ? 1 : 0;
+        }
         // static shared-memory schedule of every work item: chunks are placed in a circular byte
         // buffer in issue order; a chunk that does not fit waits for the oldest live chunks
         for (size_t it = 0; it + 1 < P.witem_ptr.size(); ++it) {

@@ -111,6 +111,7 @@ struct HostPlan {
     int64_t n_warp_slices = 0;          // follow the fused slices; the rest go to gather_gemv_kernel
     std::vector<bsm_wchunk> wchunk;     // chunk stream of the warp slices, in slice order
     std::vector<int32_t> witem_ptr;     // warp work items: chunk ranges cut at segment boundaries
+    int wform = 2;                      // forms of the warp-stream chunks: 0 N-form only, 1 T-form only, 2 both
     bool wcta = false;                  // small problems: every segment is ONE CTA of stream_warp_kernel, its chunk list
                                         // dealt to the kWItemsPerCta warps (items 4c .. 4c+3 = the parts of segment c,
                                         // possibly empty); single launch, no partial sums through global memory

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--sweep", default="", help="ENVVAR=v1,v2,...: rebuild the slab handle under every value of a tuning "
+                                                "variable (BSM_TUNE_SPLIT_DIV, BSM_TUNE_WITEMS_PER_SLOT) and time it")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -65,6 +67,17 @@ def main():
         return [round(float(o.item()), 4) for o in out]
 
     res = {"workload": spec["desc"], "n_gpus": world, "own_rows": list(map(int, SM.own))}
+    if args.sweep:
+        var, vals = args.sweep.split("=")
+        res["sweep"] = {}
+        for v in vals.split(","):
+            os.environ[var] = v
+            S2 = SlabMatrix(A, comm, ops=(op,)) if rb is None else SlabMatrix(A, comm, cuts=rb)
+            res["sweep"][f"{var}={v}"] = {"peer": max(timed(lambda: S2.mul_peer(op, xs, y), args.steps)),
+                                          "local_kernel_only": max(timed(lambda: S2.local.mul(op, x_rep, y), args.steps)),
+                                          "slices": S2.local.plan_stats(op)["slices"], "warp_items": S2.local.plan_stats(op)["warp_items"]}
+            del S2
+        os.environ.pop(var, None)
     for name, flags in (("peer", 0), ("peer_no_entry_wait", 1), ("peer_no_exit_wait", 2), ("peer_no_waits", 3),
                         ("peer_release_signals", 16), ("peer_every_arrival_waits_sys", 4), ("peer_timed", 8)):
         comm.set_debug(flags)
