@@ -1099,12 +1099,22 @@ __device__ __forceinline__ void wchunk_compute(const T *__restrict__ sm, const T
     }
 }
 
+struct WarpEnd {      // CTA-part mode: what a warp's part ended with (shared memory, one record per warp)
+    int64_t out;
+    uint32_t fl;
+    int32_t L;
+};
+
+template <class T>
+__host__ __device__ constexpr size_t stream_warp_smem_per_warp() {
+    return (size_t)kWRing + (size_t)kWDSlots * kWDBatch * 32 + 2 * kWSegMax * sizeof(T) + 8 * (kWNB + kWDSlots);
+}
 // FORM: 0 = the launch holds N-form chunks only, 1 = T-form only, 2 = both (the dead path is compiled out: half the
 // code, which matters for small problems whose first wave also pays the instruction fetch)
 template <class T, bool CONJ, int FORM>
 __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned char *ring, const int4 *dring,
                                                  T *xs, T *ts, uint64_t *full, uint64_t *dbar, int32_t q0,
-                                                 int32_t n, T *cta_part, uint32_t &end_fl, int64_t &end_out, int32_t &end_L) {
+                                                 int32_t n) {
     const int lane = threadIdx.x & 31;
     const uint64_t policy = l2_evict_first_policy();
     const int32_t nbatch = (n + kWDBatch - 1) / kWDBatch;
@@ -1214,10 +1224,14 @@ __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned 
                 if (r < L) {
                     const T tot = El<T>::add(h ? acc1 : acc0, ts[r]);
                     if (fl & 64u) {          // part of a segment: the CTA sums the parts (stream_warp_kernel)
-                        cta_part[r] = tot;
-                        end_fl = fl;
-                        end_out = o;
-                        end_L = L;
+                        // addresses recomputed here (rare path) so that nothing stays live across the chunk loop
+                        const int warp = threadIdx.x >> 5;
+                        unsigned char *tail = ring + (kWWarps - warp) * stream_warp_smem_per_warp<T>();
+                        reinterpret_cast<T *>(tail)[warp * kWSegMax + r] = tot;
+                        WarpEnd *we = reinterpret_cast<WarpEnd *>(tail + kWWarps * kWSegMax * sizeof(T)) + warp;
+                        we->out = o;
+                        we->fl = fl;
+                        we->L = L;
                     } else if (fl & 32u) {
                         const int32_t row = (fl & 4u) ? __ldg(a.pool + o + r) : (int32_t)o + r;
                         T v = El<T>::mul(a.alpha, tot);
@@ -1236,12 +1250,8 @@ __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned 
 }
 
 template <class T>
-__host__ __device__ constexpr size_t stream_warp_smem_per_warp() {
-    return (size_t)kWRing + (size_t)kWDSlots * kWDBatch * 32 + 2 * kWSegMax * sizeof(T) + 8 * (kWNB + kWDSlots);
-}
-template <class T>
 constexpr size_t stream_warp_smem_bytes() {
-    return kWWarps * stream_warp_smem_per_warp<T>() + kWWarps * kWSegMax * sizeof(T) + 16;   // + the parts of CTA-part mode
+    return kWWarps * stream_warp_smem_per_warp<T>() + kWWarps * kWSegMax * sizeof(T) + kWWarps * sizeof(WarpEnd);   // + the parts of CTA-part mode
 }
 
 template <class T, int FORM>
@@ -1263,11 +1273,9 @@ __global__ void __launch_bounds__(kWWarps * 32) stream_warp_kernel(const WarpArg
         __syncwarp();
     }
     T *parts = reinterpret_cast<T *>(wsm + kWWarps * stream_warp_smem_per_warp<T>());
-    int32_t *valid = reinterpret_cast<int32_t *>(parts + kWWarps * kWSegMax);
-    uint32_t end_fl = 0;
-    int64_t end_out = 0;
-    int32_t end_L = 0;
-    bool has_work = false;
+    WarpEnd *ends = reinterpret_cast<WarpEnd *>(parts + kWWarps * kWSegMax);
+    if (a.cta_mode && lane == 0) ends[warp].L = -1;      // no part yet
+    __syncwarp();
     if (item < a.nitems) {
         unsigned char *base = wsm + warp * stream_warp_smem_per_warp<T>();
         unsigned char *ring = base;
@@ -1284,40 +1292,36 @@ __global__ void __launch_bounds__(kWWarps * 32) stream_warp_kernel(const WarpArg
         __syncwarp();
         const int32_t q0 = __ldg(a.item_ptr + item), q1 = __ldg(a.item_ptr + item + 1);
         if (q0 < q1) {
-            has_work = true;
             bool conj_done = false;
             if constexpr (sizeof(T) == 16) {       // conj is the identity for real element types: one instantiation
                 if (a.conj) {
-                    stream_warp_body<T, true, FORM>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0, parts + warp * kWSegMax,
-                                                    end_fl, end_out, end_L);
+                    stream_warp_body<T, true, FORM>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0);
                     conj_done = true;
                 }
             }
-            if (!conj_done)
-                stream_warp_body<T, false, FORM>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0, parts + warp * kWSegMax,
-                                                 end_fl, end_out, end_L);
+            if (!conj_done) stream_warp_body<T, false, FORM>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0);
         }
     }
     if (a.cta_mode) {
         // the parts of the segment meet here: fixed order (warp 0, 1, 2, 3), one writer
-        if (lane == 0) valid[warp] = has_work ? 1 : 0;
         __syncthreads();
-        if (warp == 0 && has_work) {
+        const WarpEnd e0 = ends[0];
+        if (warp == 0 && e0.L >= 0) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int32_t r = lane + 32 * h;
-                if (r < end_L) {
+                if (r < e0.L) {
                     T tot = parts[r];
 #pragma unroll
                     for (int w = 1; w < kWWarps; ++w)
-                        if (valid[w]) tot = El<T>::add(tot, parts[w * kWSegMax + r]);
-                    if (end_fl & 32u) {
-                        const int32_t row = (end_fl & 4u) ? __ldg(a.pool + end_out + r) : (int32_t)end_out + r;
+                        if (ends[w].L >= 0) tot = El<T>::add(tot, parts[w * kWSegMax + r]);
+                    if (e0.fl & 32u) {
+                        const int32_t row = (e0.fl & 4u) ? __ldg(a.pool + e0.out + r) : (int32_t)e0.out + r;
                         T v = El<T>::mul(a.alpha, tot);
                         if (!a.beta_false) v = El<T>::add(v, El<T>::mul(a.beta, a.y[row]));
                         a.y[row] = v;
                     } else {
-                        a.scratch[end_out + r] = tot;
+                        a.scratch[e0.out + r] = tot;
                     }
                 }
             }

@@ -477,6 +477,71 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
         if (ca == 1) return false;
         return a.work > b.work;
     });
+    // 6b. single-wave regime of the warp-stream kernel (the warp slices of this handle stream less than ~768 MB, e.g. a
+    //     slab of C3 on 8 GPUs): ONE work item per resident warp slot. A slot's share is then only a few segments, and
+    //     cutting the segment list into contiguous runs leaves the heaviest item at 1.7 x the mean (measured: 58 us against
+    //     37 us at the roofline) — so the segments are PACKED into the items instead: longest processing time first onto
+    //     the lightest item (cost = bytes + 1 KB per chunk, the chunk's fixed instruction cost). The items of the local
+    //     and of the remote group are packed separately (the local ones run while x is gathered on the NCCL path).
+    std::vector<int64_t> witem_cut_after;      // positions (in the final slice order) after which a work item ends
+    if (!P.wcta && pp.witem_bytes <= 0) {
+        size_t w0 = 0;
+        while (w0 < tmp.size() && cls(tmp[w0]) != 1) ++w0;
+        size_t w1 = w0;
+        int64_t wbytes = 0;
+        while (w1 < tmp.size() && cls(tmp[w1]) == 1) wbytes += tmp[w1++].work;
+        const int64_t per_slot = pp.witems_per_slot > 0 ? pp.witems_per_slot : (wbytes < ((int64_t)768 << 20) ? 1 : 3);
+        if (w1 > w0 && per_slot == 1) {
+            auto cost_of = [&](const Tmp &t) {
+                int64_t c = 0;
+                for (int32_t k = t.s.c_begin; k < t.s.c_end; ++k) {
+                    const int64_t bytes = (int64_t)P.contrib[k].m * P.contrib[k].n * s;
+                    c += bytes + 1024 * std::max<int64_t>((bytes + kWChunkBytes - 1) / kWChunkBytes, (P.contrib[k].n + kWMaxCols - 1) / kWMaxCols);
+                }
+                return c;
+            };
+            std::vector<Tmp> packed;
+            packed.reserve(w1 - w0);
+            const int64_t slots = 148 * 16;
+            int64_t cost_grp[2] = {0, 0};
+            for (size_t i = w0; i < w1; ++i) cost_grp[tmp[i].remote ? 1 : 0] += cost_of(tmp[i]);
+            const int64_t allcost = std::max<int64_t>(cost_grp[0] + cost_grp[1], 1);
+            // the slots are shared between the groups in proportion to their cost; together never more than one wave
+            int64_t bins_grp[2];
+            bins_grp[0] = cost_grp[1] == 0 ? slots : std::max<int64_t>(cost_grp[0] > 0 ? 1 : 0, slots * cost_grp[0] / allcost);
+            bins_grp[1] = cost_grp[1] == 0 ? 0 : std::max<int64_t>(1, slots - bins_grp[0]);
+            for (int grp = 0; grp < 2; ++grp) {       // 0: local, 1: remote
+                std::vector<size_t> idx;
+                for (size_t i = w0; i < w1; ++i)
+                    if ((int)tmp[i].remote == grp) idx.push_back(i);
+                if (idx.empty()) continue;
+                const int64_t nbins = std::max<int64_t>(1, std::min<int64_t>((int64_t)idx.size(), bins_grp[grp]));
+                std::vector<size_t> order(idx);
+                std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return cost_of(tmp[a]) > cost_of(tmp[b]); });
+                std::vector<int64_t> load((size_t)nbins, 0);
+                std::vector<std::vector<size_t>> bins((size_t)nbins);
+                // lightest bin first; ties broken by bin index, so the packing is deterministic
+                std::vector<std::pair<int64_t, int64_t>> heap;
+                for (int64_t b = 0; b < nbins; ++b) heap.emplace_back(0, b);
+                auto cmp = [](const std::pair<int64_t, int64_t> &a, const std::pair<int64_t, int64_t> &b) { return a > b; };
+                std::make_heap(heap.begin(), heap.end(), cmp);
+                for (size_t i : order) {
+                    std::pop_heap(heap.begin(), heap.end(), cmp);
+                    auto &top = heap.back();
+                    bins[(size_t)top.second].push_back(i);
+                    top.first += cost_of(tmp[i]);
+                    std::push_heap(heap.begin(), heap.end(), cmp);
+                }
+                for (auto &bin : bins) {
+                    if (bin.empty()) continue;
+                    std::sort(bin.begin(), bin.end());          // arena order inside an item
+                    for (size_t i : bin) packed.push_back(tmp[i]);
+                    witem_cut_after.push_back((int64_t)(w0 + packed.size() - 1));
+                }
+            }
+            std::copy(packed.begin(), packed.end(), tmp.begin() + (long)w0);
+        }
+    }
     P.slices.reserve(tmp.size());
     for (const auto &t : tmp) {
         P.slices.push_back(t.s);
@@ -608,7 +673,10 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
             // work items never mix local and remote segments: the local items run while x is gathered
             const bool last_local = !(sl.flags & kSliceRemote) && i + 1 < P.n_fused_slices + P.n_warp_slices &&
                                     (P.slices[i + 1].flags & kSliceRemote);
-            if (item_bytes >= target || last_local) {
+            bool cut_here = item_bytes >= target || last_local;
+            if (!witem_cut_after.empty())      // packed items: the cuts were decided in step 6b
+                cut_here = std::binary_search(witem_cut_after.begin(), witem_cut_after.end(), i);
+            if (cut_here) {
                 P.witem_ptr.push_back((int32_t)P.wchunk.size());
                 item_bytes = 0;
             }
