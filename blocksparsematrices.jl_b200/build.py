@@ -14,7 +14,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libbsm_b200.so"
 SOURCES = ["abi.cu", "dist.cu", "sparse.cu", "krylov.cu", "construct.cu", "pack.cpp"]
-DEPS = ["kernels.cuh", "spmm.cuh", "spmm_tma.cuh", "spmm_layout.h", "plan.h", "../../include/bsm_b200.h"]
+DEPS = ["kernels.cuh", "persist.cuh", "spmm.cuh", "spmm_tma.cuh", "spmm_layout.h", "plan.h", "../../include/bsm_b200.h"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "persist.cuh"
 #include "plan.h"
 #include "spmm.cuh"
 #include "spmm_tma.cuh"
@@ -414,6 +415,16 @@ int plan_index(const bsm_matrix *A, int op) {
     return base + (fused ? 2 : 0);
 }
 
+int sm_count(int device) {
+    static int cached[64] = {};
+    int &c = cached[device & 63];
+    if (c == 0) {
+        int v = 0;
+        c = (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ? v : 148;
+    }
+    return c;
+}
+
 // Persistent partial-sum scratch of (handle, stream): allocated on the first multiply a stream sees.
 int get_scratch(bsm_matrix *A, cudaStream_t st, void **out) {
     *out = nullptr;
@@ -448,6 +459,8 @@ int ensure_attrs(int device) {
                                   (int)fused_tma_smem_bytes<T>()));
     CUDA_TRY(cudaFuncSetAttribute(sym_fused_tma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fused_tma_smem_bytes<T>()));
+    CUDA_TRY(cudaFuncSetAttribute(sym_persist_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)PersistSmem<T>::total));
     CUDA_TRY(cudaFuncSetAttribute(stream_warp_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)stream_warp_smem_bytes<T>()));
     CUDA_TRY(cudaFuncSetAttribute(stream_warp_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -785,8 +798,14 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             if (use_tma)
                 if (HP.fused_general)
                     sym_fused_tma_kernel<T, true><<<f1 - f0, kPThreads, fused_tma_smem_bytes<T>(), st>>>(b);
-                else
+                else if (A->variant == BSM_VARIANT_FUSED_TMA)      // comparison: one CTA per work item
                     sym_fused_tma_kernel<T, false><<<f1 - f0, kPThreads, fused_tma_smem_bytes<T>(), st>>>(b);
+                else {
+                    // persistent CTAs (two per SM) walking the work items, helpers staging x and metadata ahead
+                    b.nslices = f1 - f0;
+                    if (b.x.npeer && last_kind == 0) b.x.sync.arrivals = std::min<int32_t>(f1 - f0, 2 * sm_count(A->device));
+                    sym_persist_kernel<T><<<std::min<int32_t>(f1 - f0, 2 * sm_count(A->device)), kQThreads, PersistSmem<T>::total, st>>>(b);
+                }
             else
                 sym_fused_kernel<T><<<f1 - f0, kFThreads, fused_smem_bytes<T>(), st>>>(b);
             CUDA_TRY(cudaGetLastError());

@@ -137,6 +137,11 @@ class SlabMatrix:
         self.own = (lo, hi)
         self.local = DeviceMatrix(A, device=comm.device, variant=variant, own_rows=(lo, hi), own_cols=(lo, hi))
         self.dtype = self.local.dtype
+        # marshalled once: a multiply on 8 GPUs lasts tens of microseconds, the call must not cost as much
+        self._one = np.array([1], dtype=self.dtype)
+        self._zero = np.array([0], dtype=self.dtype)
+        self._cuts_p = self.cuts.ctypes.data_as(POINTER(c_int64))
+        self._fn_peer = L.lib().bsm_mul_dist_peer
 
     def mul(self, op, x, y, alpha=True, beta=False, stream=None):
         import torch
@@ -162,16 +167,16 @@ class SlabMatrix:
         (bsm_mul_dist_peer: flag barrier, multiply, flag barrier)."""
         import torch
         D = self.local
-        beta_false = isinstance(beta, (bool, np.bool_)) and not beta
-        a = np.array([alpha], dtype=D.dtype)
-        b = np.array([0 if beta_false else beta], dtype=D.dtype)
+        beta_false = beta is False or (isinstance(beta, np.bool_) and not beta)
+        a = self._one if alpha is True else np.array([alpha], dtype=D.dtype)
+        b = self._zero if beta_false else np.array([beta], dtype=D.dtype)
         if x_shared.dim() != 1 or x_shared.dtype != _torch_dtype(D.dtype) or y.dtype != x_shared.dtype:
             raise TypeError("x and y must be 1-D CUDA tensors of the operator's dtype")
         st = torch.cuda.current_stream(x_shared.device).cuda_stream if stream is None else stream
-        L.check(L.lib().bsm_mul_dist_peer(self.comm._h, D._h, _OPS[op], a.ctypes.data_as(c_void_p),
-                                          b.ctypes.data_as(c_void_p), int(beta_false), c_void_p(x_shared.data_ptr()),
-                                          c_void_p(y.data_ptr()), self.cuts.ctypes.data_as(POINTER(c_int64)),
-                                          c_void_p(st)))
+        rc = self._fn_peer(self.comm._h, D._h, _OPS[op], a.ctypes.data, b.ctypes.data, int(beta_false),
+                           x_shared.data_ptr(), y.data_ptr(), self._cuts_p, st)
+        if rc:
+            L.check(rc)
         return y
 
     def mul_peer_host(self, op, x_host_slab, x_shared, y_dev, y_host_slab, alpha=True, beta=False, stream=None):
