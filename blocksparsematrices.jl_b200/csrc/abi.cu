@@ -108,6 +108,7 @@ struct bsm_matrix {
     void *sparse_slot[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool restricted = false;
     bool blocks_on_device = false;  // the block sources of the pending upload are device pointers
+    int64_t plan_hints = 0;
     // tensor maps of the arena for spmm_tma_kernel (encoded on the first multi-RHS multiply)
     TmaMaps tma_maps;
     bool tma_maps_ready = false;
@@ -345,6 +346,7 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
         A->variant = opt->variant;
         A->restricted = opt->own_row_hi >= 0 || opt->own_col_hi >= 0;
         A->blocks_on_device = opt->blocks_on_device != 0;
+        A->plan_hints = opt->plan_hints;
     }
     // work-item budget of the stream plans: no CTA should hold more than ~1/8 of a resident slot's fair share (LPT tail <= ~6 %)
     const int64_t total_bytes = [&] {
@@ -798,13 +800,18 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             if (use_tma)
                 if (HP.fused_general)
                     sym_fused_tma_kernel<T, true><<<f1 - f0, kPThreads, fused_tma_smem_bytes<T>(), st>>>(b);
-                else if (A->variant == BSM_VARIANT_FUSED_TMA)      // comparison: one CTA per work item
+                else if (!(A->plan_hints & 8) && !(std::getenv("BSM_TUNE_PERSIST") && std::atoi(std::getenv("BSM_TUNE_PERSIST"))))   // default: one CTA per work item
                     sym_fused_tma_kernel<T, false><<<f1 - f0, kPThreads, fused_tma_smem_bytes<T>(), st>>>(b);
                 else {
-                    // persistent CTAs (two per SM) walking the work items, helpers staging x and metadata ahead
+                    // experimental (plan_hints bit 3 / BSM_TUNE_PERSIST): persistent CTAs (two per SM) walking the work
+                    // items, helper warps staging x and metadata ahead — correct, but 5-7 % slower than the per-item CTAs on
+                    // C2 (profiles/README.md, "measured and rejected")
                     b.nslices = f1 - f0;
-                    if (b.x.npeer && last_kind == 0) b.x.sync.arrivals = std::min<int32_t>(f1 - f0, 2 * sm_count(A->device));
-                    sym_persist_kernel<T><<<std::min<int32_t>(f1 - f0, 2 * sm_count(A->device)), kQThreads, PersistSmem<T>::total, st>>>(b);
+                    const char *tune_grid = std::getenv("BSM_TUNE_PERSIST_CTAS_PER_SM");   // 0: one CTA per item
+                    const int per_sm = tune_grid ? std::atoi(tune_grid) : 2;
+                    const int32_t pgrid = per_sm > 0 ? std::min<int32_t>(f1 - f0, per_sm * sm_count(A->device)) : f1 - f0;
+                    if (b.x.npeer && last_kind == 0) b.x.sync.arrivals = pgrid;
+                    sym_persist_kernel<T><<<pgrid, kQThreads, PersistSmem<T>::total, st>>>(b);
                 }
             else
                 sym_fused_kernel<T><<<f1 - f0, kFThreads, fused_smem_bytes<T>(), st>>>(b);

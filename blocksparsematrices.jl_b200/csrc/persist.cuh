@@ -70,10 +70,27 @@ __device__ __forceinline__ void persist_issuer(const MulArgs<T> &a, unsigned cha
     const uint64_t policy = l2_evict_first_policy();
     uint32_t q = 0;
     const int32_t nit = persist_item_count(a.nslices);
+    // metadata is fetched one step ahead (next slice, next contribution): the loads are in flight while the chunks of
+    // the current block are issued, so the ring never drains at an item or block boundary
+    bsm_slice sl_next = nit > 0 ? a.slices[persist_item(0, a.nslices)] : bsm_slice{};
+    bsm_contrib cb_next = bsm_contrib{};
+    int32_t ci_next = -1;          // which contribution cb_next holds
+    if (nit > 0 && sl_next.c_begin < sl_next.c_end) {
+        ci_next = sl_next.c_begin;
+        cb_next = a.contrib[ci_next];
+    }
     for (int32_t k = 0; k < nit; ++k) {
-        const bsm_slice sl = a.slices[persist_item(k, a.nslices)];
+        const bsm_slice sl = sl_next;
+        if (k + 1 < nit) sl_next = a.slices[persist_item(k + 1, a.nslices)];
         for (int32_t ci = sl.c_begin; ci < sl.c_end; ++ci) {
-            const bsm_contrib cb = a.contrib[ci];
+            const bsm_contrib cb = (ci_next == ci) ? cb_next : a.contrib[ci];
+            if (ci + 1 < sl.c_end)
+                ci_next = ci + 1;
+            else if (k + 1 < nit && sl_next.c_begin < sl_next.c_end)
+                ci_next = sl_next.c_begin;
+            else
+                ci_next = -1;
+            if (ci_next >= 0) cb_next = a.contrib[ci_next];
             const int32_t m = cb.m;
             const bool tform = (cb.form & 1) != 0;
             const int32_t jhi = tform ? min(sl.r1, cb.out_len) : cb.n;
@@ -94,6 +111,27 @@ __device__ __forceinline__ void persist_issuer(const MulArgs<T> &a, unsigned cha
                     bulk_g2s(stages + stage * kPStageBytes, blk + (boff - delta), bytes, &full[stage], policy);
                 }
             }
+        }
+    }
+}
+
+// Gathers n (<= 512) entries dst[i] = i < nvalid ? x[idx(i0 + i)] : 0 with the 32 lanes of the stager warp: the loads of
+// a batch are all issued before the first store, so a window costs one memory round trip, not n/32 of them.
+template <class T>
+__device__ __forceinline__ void stage_gather(const MulArgs<T> &a, const SetRef &set, int32_t i0, int32_t nvalid, int32_t n,
+                                             T *dst, int lane) {
+    constexpr int B = 8;
+    for (int32_t base = 0; base < n; base += 32 * B) {
+        T v[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const int32_t i = base + u * 32 + lane;
+            v[u] = (i < nvalid) ? a.x.at(set.at(i0 + i)) : El<T>::zero();
+        }
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const int32_t i = base + u * 32 + lane;
+            if (i < n) dst[i] = v[u];
         }
     }
 }
@@ -131,15 +169,12 @@ __device__ __forceinline__ void persist_stager(const MulArgs<T> &a, T *xbuf, T *
                 const uint32_t b = w & 1;
                 if (w >= 2) mbar_wait(&xempty[b], ((w >> 1) - 1) & 1);
                 T *xs = xbuf + b * kQWin;
-                if (tform) {        // x at the block's rows, zero-padded to the rows the lanes hold
-                    for (int32_t i = lane; i < kFMaxRows; i += 32) xs[i] = (i < m) ? a.x.at(in.at(i)) : El<T>::zero();
-                } else {
-                    for (int32_t i = lane; i < wend - jw; i += 32) xs[i] = a.x.at(in.at(jw + i));
-                }
-                if (first) {        // x at the segment's own rows (read by the fused transposed partials of this item)
-                    T *xr = xrs + (k & 1) * kFMaxRows;
-                    for (int32_t i = lane; i < kFMaxRows; i += 32) xr[i] = (i < L) ? a.x.at(out.at(i)) : El<T>::zero();
-                }
+                if (tform)          // x at the block's rows, zero-padded to the rows the lanes hold
+                    stage_gather<T>(a, in, 0, m, kFMaxRows, xs, lane);
+                else if (wend > jw)
+                    stage_gather<T>(a, in, jw, wend - jw, wend - jw, xs, lane);
+                if (first)          // x at the segment's own rows (read by the fused transposed partials of this item)
+                    stage_gather<T>(a, out, 0, L, kFMaxRows, xrs + (k & 1) * kFMaxRows, lane);
                 if (lane == 0) {
                     WinDesc d;
                     d.m = m;
@@ -165,99 +200,101 @@ __device__ __forceinline__ void persist_stager(const MulArgs<T> &a, T *xbuf, T *
     }
 }
 
-// consume_chunk on the first RPL of the RPLMAX row sums a lane holds (register moves only)
-template <class T, int RPL, int RPLMAX, bool CONJ>
-__device__ __forceinline__ void consume_sub(const T *sm, int32_t m, int32_t ncols, int lane, int wrot, bool doN, bool doT,
-                                            const T *xcol, const T *xrow, T (&accN)[RPLMAX], T *tglobal, T *tsmem) {
-    T acc[RPL];
-#pragma unroll
-    for (int k = 0; k < RPL; ++k) acc[k] = accN[k];
-    consume_chunk<T, RPL, CONJ>(sm, m, ncols, lane, wrot, doN, doT, xcol, xrow, acc, tglobal, tsmem);
-#pragma unroll
-    for (int k = 0; k < RPL; ++k) accN[k] = acc[k];
-}
+struct PersistCursor {      // what a consumer carries from item to item
+    uint32_t q, pbase, w, item;
+};
 
-template <class T, int RPLMAX, bool CONJ>
-__device__ __forceinline__ void persist_consumer(const MulArgs<T> &a, unsigned char *stages, const T *xbuf, const T *xrs_all,
-                                                 T *accT, const WinDesc *wd, uint64_t *full, uint64_t *empty, uint64_t *xfull,
-                                                 uint64_t *xempty) {
+// One work item on the consumer side, compiled per rows-per-lane (RPL = 2 / 4 / 8 for segments of <= 64 / 128 / 256 rows):
+// the row sums live only inside this function, so every instantiation gets the register allocation of the round-1
+// per-CTA consumer (a single body with a run-time RPL kept eight row sums live everywhere and spilled in the hot loop:
+// C2 1.97 -> 2.8 ms, measured). `d` is the item's first window descriptor, already waited for. Returns true when the
+// CTA's work is finished.
+template <class T, int RPL, bool CONJ>
+__device__ __forceinline__ bool persist_item_body(const MulArgs<T> &a, unsigned char *stages, const T *xbuf, const T *xrs_all,
+                                                  T *accT, const WinDesc *wd, uint64_t *full, uint64_t *empty, uint64_t *xfull,
+                                                  uint64_t *xempty, WinDesc d, PersistCursor &cur) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (persist_item_count(a.nslices) == 0) return;
-    T accN[RPLMAX];
-    uint32_t q = 0, pbase = 0, w = 0, item = 0;
-    accT[t] = El<T>::zero();
-    consumer_bar();
-    for (;;) {
-        const uint32_t b = w & 1;
-        mbar_wait(&xfull[b], (w >> 1) & 1);
-        const WinDesc d = wd[b];
-        const T *xs = xbuf + b * kQWin;
-        const T *xrs = xrs_all + (item & 1) * kFMaxRows;
-        if (d.flags & 4) {
+    T accN[RPL];
 #pragma unroll
-            for (int k = 0; k < RPLMAX; ++k) accN[k] = El<T>::zero();
-        }
+    for (int k = 0; k < RPL; ++k) accN[k] = El<T>::zero();
+    const T *xrs = xrs_all + (cur.item & 1) * kFMaxRows;
+    for (;;) {
+        const uint32_t b = cur.w & 1;
+        const T *xs = xbuf + b * kQWin;
         const int32_t m = d.m;
         if (m > 0 && d.wcols > 0) {
             const int32_t cc = chunk_cols<T>(m);
             const bool tform = (d.flags & 1) != 0, fusedT = (d.flags & 2) != 0;
             T *tg = fusedT ? a.scratch + d.toff : nullptr;
-            const int32_t L = d.L;
-            for (int32_t j0 = 0; j0 < d.wcols; j0 += cc, ++q) {
+            for (int32_t j0 = 0; j0 < d.wcols; j0 += cc, ++cur.q) {
                 const int32_t ncols = min(cc, d.wcols - j0);
-                const uint32_t stage = q % kPStages;
+                const uint32_t stage = cur.q % kPStages;
                 const uint32_t delta = (uint32_t)(((int64_t)(d.jw + j0) * m * (int64_t)sizeof(T)) & 15);
-                mbar_wait(&full[stage], (q / kPStages) & 1);
+                mbar_wait(&full[stage], (cur.q / kPStages) & 1);
                 const T *sm = reinterpret_cast<const T *>(stages + stage * kPStageBytes + delta);
-                const int wrot = (warp - pbase) & (kFWarps - 1);
-                // rows held per lane follow the segment length (fewer FMAs on short segments), as in sym_fused_tma_kernel
-                T *tgl = (!tform && fusedT) ? tg + d.jw + j0 : nullptr;
-                T *tsm = tform ? accT + j0 : nullptr;
-                const T *xc = tform ? nullptr : xs + j0;
-                const T *xr = tform ? xs : xrs;
-                if (L <= 64)
-                    consume_sub<T, 2, RPLMAX, CONJ>(sm, m, ncols, lane, wrot, !tform, tform || fusedT, xc, xr, accN, tgl, tsm);
-                else if (L <= 128)
-                    consume_sub<T, 4, RPLMAX, CONJ>(sm, m, ncols, lane, wrot, !tform, tform || fusedT, xc, xr, accN, tgl, tsm);
+                const int wrot = (warp - cur.pbase) & (kFWarps - 1);
+                if (tform)
+                    consume_chunk<T, RPL, CONJ>(sm, m, ncols, lane, wrot, false, true, nullptr, xs, accN, nullptr, accT + j0);
                 else
-                    consume_sub<T, 8, RPLMAX, CONJ>(sm, m, ncols, lane, wrot, !tform, tform || fusedT, xc, xr, accN, tgl, tsm);
-                pbase += (uint32_t)((ncols + 1) >> 1);
+                    consume_chunk<T, RPL, CONJ>(sm, m, ncols, lane, wrot, true, fusedT, xs + j0, xrs, accN,
+                                                fusedT ? tg + d.jw + j0 : nullptr, nullptr);
+                cur.pbase += (uint32_t)((ncols + 1) >> 1);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[stage]);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&xempty[b]);
-        ++w;
-        if (d.flags & 8) {
-            // item complete: the eight warps add their row sums into accT in warp order, then the rows are written
-            consumer_bar();
-            const int32_t L = d.L;
-            const int rpl = L <= 64 ? 2 : (L <= 128 ? 4 : 8);
-            for (int wi = 0; wi < kFWarps; ++wi) {
-                if (warp == wi) {
+        ++cur.w;
+        if (d.flags & 8) break;
+        mbar_wait(&xfull[cur.w & 1], (cur.w >> 1) & 1);
+        d = wd[cur.w & 1];
+    }
+    // item complete: the eight warps add their row sums into accT in warp order, then the rows are written
+    consumer_bar();
+    for (int wi = 0; wi < kFWarps; ++wi) {
+        if (warp == wi) {
 #pragma unroll
-                    for (int k = 0; k < RPLMAX; ++k)
-                        if (k < rpl) accT[k * 32 + lane] = El<T>::add(accT[k * 32 + lane], accN[k]);
-                }
-                consumer_bar();
-            }
-            if (t < L) {
-                const T tot = accT[t];
-                if (d.flags & 16) {
-                    const int32_t row = d.out_start >= 0 ? d.out_start + t : __ldg(a.pool + d.out_pool + t);
-                    T v = El<T>::mul(a.alpha, tot);
-                    if (!a.beta_false) v = El<T>::add(v, El<T>::mul(a.beta, a.y[row]));
-                    a.y[row] = v;
-                } else {
-                    a.scratch[d.scratch_off + t] = tot;
-                }
-            }
-            accT[t] = El<T>::zero();
-            consumer_bar();
-            ++item;
-            if (d.flags & 32) break;
+            for (int k = 0; k < RPL; ++k) accT[k * 32 + lane] = El<T>::add(accT[k * 32 + lane], accN[k]);
         }
+        consumer_bar();
+    }
+    if (t < d.L) {
+        const T tot = accT[t];
+        if (d.flags & 16) {
+            const int32_t row = d.out_start >= 0 ? d.out_start + t : __ldg(a.pool + d.out_pool + t);
+            T v = El<T>::mul(a.alpha, tot);
+            if (!a.beta_false) v = El<T>::add(v, El<T>::mul(a.beta, a.y[row]));
+            a.y[row] = v;
+        } else {
+            a.scratch[d.scratch_off + t] = tot;
+        }
+    }
+    accT[t] = El<T>::zero();
+    consumer_bar();
+    ++cur.item;
+    return (d.flags & 32) != 0;
+}
+
+template <class T, bool CONJ>
+__device__ __forceinline__ void persist_consumer(const MulArgs<T> &a, unsigned char *stages, const T *xbuf, const T *xrs_all,
+                                                 T *accT, const WinDesc *wd, uint64_t *full, uint64_t *empty, uint64_t *xfull,
+                                                 uint64_t *xempty) {
+    if (persist_item_count(a.nslices) == 0) return;
+    PersistCursor cur{0, 0, 0, 0};
+    accT[threadIdx.x] = El<T>::zero();
+    consumer_bar();
+    for (;;) {
+        mbar_wait(&xfull[cur.w & 1], (cur.w >> 1) & 1);
+        const WinDesc d = wd[cur.w & 1];
+        bool end;
+        if (d.L <= 64)
+            end = persist_item_body<T, 2, CONJ>(a, stages, xbuf, xrs_all, accT, wd, full, empty, xfull, xempty, d, cur);
+        else if (d.L <= 128)
+            end = persist_item_body<T, 4, CONJ>(a, stages, xbuf, xrs_all, accT, wd, full, empty, xfull, xempty, d, cur);
+        else
+            end = persist_item_body<T, 8, CONJ>(a, stages, xbuf, xrs_all, accT, wd, full, empty, xfull, xempty, d, cur);
+        if (end) break;
     }
 }
 
@@ -296,11 +333,11 @@ __global__ void __launch_bounds__(kQThreads, kQMaxCtasPerSm) sym_persist_kernel(
         bool done = false;
         if constexpr (sizeof(T) == 16) {      // conj is the identity for real element types
             if (a.conj) {
-                persist_consumer<T, 8, true>(a, stages, xbuf, xrs, accT, wd, full, empty, xfull, xempty);
+                persist_consumer<T, true>(a, stages, xbuf, xrs, accT, wd, full, empty, xfull, xempty);
                 done = true;
             }
         }
-        if (!done) persist_consumer<T, 8, false>(a, stages, xbuf, xrs, accT, wd, full, empty, xfull, xempty);
+        if (!done) persist_consumer<T, false>(a, stages, xbuf, xrs, accT, wd, full, empty, xfull, xempty);
         // every x read of this CTA (the stager's) precedes the last window the consumers waited for
         if (a.x.npeer && threadIdx.x == 0) peer_exit(a.x.sync);
     }

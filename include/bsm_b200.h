@@ -87,7 +87,8 @@ typedef struct {
     int64_t plan_hints;    /* 0 = automatic. Bits, for experiments and comparison runs: 1 = short segments go to the CTA-stream
                               kernel, not the warp-stream kernel; 2 = never cut the segments of a small (L2-resident) problem
                               into per-block work items; 4 = small problems keep the round-1 schedule (per-block work items, partial
-                              sums through scratch, gather pass) instead of the single-launch CTA-part mode */
+                              sums through scratch, gather pass) instead of the single-launch CTA-part mode; 8 = experimental persistent
+                              form of the CTA-stream kernel (sym_persist_kernel) */
     int64_t blocks_on_device; /* != 0: the block pointers handed to bsm_create_* are DEVICE pointers (blocks assembled on the
                               GPU): the arena is filled by a gather kernel in HBM, nothing crosses PCIe */
     int64_t reserved[2];

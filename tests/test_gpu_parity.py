@@ -577,3 +577,20 @@ def test_vbcrs_sorting_constructor_on_the_device():
     assert np.array_equal(rowptr.cpu().numpy(), V.rowptr) and np.array_equal(rowidx.cpu().numpy(), V.rowindices)
     assert np.array_equal(colidx.cpu().numpy(), V.colindices)
     assert np.array_equal(shuffle[perm.cpu().numpy()], np.arange(len(V.blocks)))
+
+
+def test_persistent_cta_kernel_parity():
+    """sym_persist_kernel (bsm_options.plan_hints bit 3; experimental, not the default — profiles/README.md): persistent
+    CTAs with an issuer and an x-stager warp running ahead across work items must give the same products."""
+    for A in (G.symmetric_nearfield(seed=81, n=30000, k_near=4), G.symmetric_nearfield(seed=82, n=9000, dtype=np.float32, permuted=True),
+              G.symmetric_nearfield(seed=83, n=12000, leaf_min=150, leaf_max=250, k_near=4, dtype=np.float64)):
+        D = B.DeviceMatrix(A, plan_hints=8)
+        dt = np.dtype(A.dtype)
+        rng = np.random.default_rng(6)
+        alpha, beta = (1j, 2j) if dt.kind == "c" else (0.7, -0.4)
+        for op in OPS:
+            x = randx(rng, A.size[1], dt)
+            y0 = randx(rng, A.size[0], dt)
+            f64 = dt == np.float32
+            assert rel2(D.mul(op, x), oracle_mul(A, x, op, f64=f64)) < TOL[dt], op
+            assert rel2(D.mul(op, x, y0.copy(), alpha, beta), oracle_mul(A, x, op, alpha, beta, False, y0.copy(), f64=f64)) < TOL[dt], op
