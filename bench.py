@@ -371,7 +371,7 @@ def run_workload(cx, name, primary):
     sampler = ClockSampler(local)
     if rank == 0 and primary:
         sampler.launch()
-    l2_resident = work["bytes"] <= 4 * 126e6
+    l2_resident = work["bytes"] <= 4 * 126e6 and not args.warm_l2
     # single GPU: the per-kernel event brackets are recorded IN the timed region. N > 1: a multiply lasts tens of
     # microseconds and three event records per step would leave gaps in the stream, so the kernel is timed in a
     # separate loop right after the timed region
@@ -620,6 +620,7 @@ def run_solver(cx, A, D, SM, own, host_threads, shift=400.0):
 
     # the set-up of a solve (work vectors; on N > 1 the collective allocation of the peer-mapped search direction) is
     # timed apart from the iterations: one solve cut off after 8 iterations, one to convergence
+    solve(1)                      # warm-up: first-use costs (IPC mappings, allocator) stay out of both timed solves
     _, it8, _, sec8 = solve(8)
     x, iters, rel, sec = solve(200)
     sec_it = (sec - sec8) / max(iters - it8, 1) if iters > it8 else sec / max(iters, 1)
@@ -674,6 +675,8 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="N > 1: all-gather, then multiply, on one stream")
     ap.add_argument("--op", default=None, choices=["N", "T", "C"], help="override the workload's op (development)")
     ap.add_argument("--plan-hints", type=int, default=0, help="bsm_options.plan_hints (development)")
+    ap.add_argument("--warm-l2", action="store_true", help="small workloads: do NOT flush L2 between the timed iterations "
+                                                           "(the matrix stays L2-resident, as inside a solver loop); the line says so")
     ap.add_argument("--nrhs", type=int, default=0, help="c5: number of right-hand sides (development; default 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="default workload only: skip the c3 / c5 companion results")

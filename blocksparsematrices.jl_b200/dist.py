@@ -115,33 +115,49 @@ class SlabMatrix:
     """Rank-local part of a block matrix cut into nnz-balanced block-row slabs.
 
     SlabMatrix(A, comm)                 A: the full host matrix (every rank holds it; blocks are shared,
-                                        only this rank's slab is packed into HBM)
+                                        only this rank's slab is packed into HBM). Non-square operators: rows and
+                                        columns are partitioned separately (cuts / col_cuts)
     SlabMatrix(S, comm, cuts=cuts)      S: a host container that already holds only this rank's blocks
     y = op(A) x: x is a full-length CUDA tensor of which this rank owns rows in_cuts[rank]:in_cuts[rank+1];
     mul() all-gathers it in place and writes y[out_cuts[rank]:out_cuts[rank+1]].
     """
 
-    def __init__(self, A, comm: Comm, cuts=None, ops=("N",), variant=L.VARIANT_AUTO):
+    def __init__(self, A, comm: Comm, cuts=None, ops=("N",), variant=L.VARIANT_AUTO, col_cuts=None):
         self.comm = comm
         self.size = A.size
-        if A.size[0] != A.size[1]:
-            # one set of cuts is both the partition of y (this rank's output slab) and of x (the slab it owns
-            # before the exchange): that is the solver-loop convention and needs a square operator
-            raise NotImplementedError("slab partition of a non-square operator (separate row / column cuts)")
+        square = A.size[0] == A.size[1]
         if cuts is None:
-            cuts = slab_cuts(A, comm.nranks, "N" if "N" in ops else "T")
-            lo, hi = int(cuts[comm.rank]), int(cuts[comm.rank + 1])
-            A = extract_slab(A, lo, hi, ops)
-        self.cuts = np.ascontiguousarray(cuts, np.int64)
+            # rows of y = A x and, for a non-square operator or when only transposed products are wanted, columns
+            # (= rows of y = A' x) are partitioned separately, each balanced by the bytes streamed for its outputs
+            cuts = slab_cuts(A, comm.nranks, "N" if ("N" in ops or not square) else "T")
+            if col_cuts is None and not square:
+                col_cuts = slab_cuts(A, comm.nranks, "T")
+            cc = cuts if col_cuts is None else col_cuts
+            A = extract_slab(A, int(cuts[comm.rank]), int(cuts[comm.rank + 1]), ops,
+                             cols=(int(cc[comm.rank]), int(cc[comm.rank + 1])))
+        elif not square and col_cuts is None:
+            raise ValueError("a non-square operator needs col_cuts beside the row cuts")
+        self.cuts = np.ascontiguousarray(cuts, np.int64)                    # rows: y of op N, x of op T / C
+        self.col_cuts = self.cuts if col_cuts is None else np.ascontiguousarray(col_cuts, np.int64)
         lo, hi = int(self.cuts[comm.rank]), int(self.cuts[comm.rank + 1])
+        clo, chi = int(self.col_cuts[comm.rank]), int(self.col_cuts[comm.rank + 1])
         self.own = (lo, hi)
-        self.local = DeviceMatrix(A, device=comm.device, variant=variant, own_rows=(lo, hi), own_cols=(lo, hi))
+        self.own_cols = (clo, chi)
+        self.local = DeviceMatrix(A, device=comm.device, variant=variant, own_rows=(lo, hi), own_cols=(clo, chi))
         self.dtype = self.local.dtype
         # marshalled once: a multiply on 8 GPUs lasts tens of microseconds, the call must not cost as much
         self._one = np.array([1], dtype=self.dtype)
         self._zero = np.array([0], dtype=self.dtype)
         self._cuts_p = self.cuts.ctypes.data_as(POINTER(c_int64))
+        self._col_cuts_p = self.col_cuts.ctypes.data_as(POINTER(c_int64))
         self._fn_peer = L.lib().bsm_mul_dist_peer
+
+    def in_cuts_p(self, op):
+        """x of op N is partitioned like the columns, x of op T / C like the rows."""
+        return self._col_cuts_p if op == "N" else self._cuts_p
+
+    def out_range(self, op):
+        return self.own if op == "N" else self.own_cols
 
     def mul(self, op, x, y, alpha=True, beta=False, stream=None):
         import torch
@@ -157,8 +173,7 @@ class SlabMatrix:
         st = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
         L.check(L.lib().bsm_mul_dist(self.comm._h, D._h, _OPS[op], a.ctypes.data_as(c_void_p),
                                      b.ctypes.data_as(c_void_p), int(beta_false), c_void_p(x.data_ptr()), ldx,
-                                     c_void_p(y.data_ptr()), ldy, nrhs,
-                                     self.cuts.ctypes.data_as(POINTER(c_int64)), c_void_p(st)))
+                                     c_void_p(y.data_ptr()), ldy, nrhs, self.in_cuts_p(op), c_void_p(st)))
         return y
 
     def mul_peer(self, op, x_shared, y, alpha=True, beta=False, stream=None):
@@ -174,7 +189,7 @@ class SlabMatrix:
             raise TypeError("x and y must be 1-D CUDA tensors of the operator's dtype")
         st = torch.cuda.current_stream(x_shared.device).cuda_stream if stream is None else stream
         rc = self._fn_peer(self.comm._h, D._h, _OPS[op], a.ctypes.data, b.ctypes.data, int(beta_false),
-                           x_shared.data_ptr(), y.data_ptr(), self._cuts_p, st)
+                           x_shared.data_ptr(), y.data_ptr(), self.in_cuts_p(op), st)
         if rc:
             L.check(rc)
         return y
@@ -187,8 +202,9 @@ class SlabMatrix:
         beta_false = isinstance(beta, (bool, np.bool_)) and not beta
         a = np.array([alpha], dtype=D.dtype)
         b = np.array([0 if beta_false else beta], dtype=D.dtype)
-        lo, hi = self.own
-        if x_host_slab.dtype != D.dtype or y_host_slab.dtype != D.dtype or len(x_host_slab) != hi - lo or \
+        lo, hi = self.out_range(op)
+        ilo, ihi = self.own_cols if op == "N" else self.own
+        if x_host_slab.dtype != D.dtype or y_host_slab.dtype != D.dtype or len(x_host_slab) != ihi - ilo or \
                 len(y_host_slab) != hi - lo:
             raise ValueError("DimensionMismatch: host slabs must hold this rank's rows in the operator's dtype")
         st = torch.cuda.current_stream(x_shared.device).cuda_stream if stream is None else stream
@@ -196,7 +212,7 @@ class SlabMatrix:
                                                b.ctypes.data_as(c_void_p), int(beta_false),
                                                x_host_slab.ctypes.data_as(c_void_p), c_void_p(x_shared.data_ptr()),
                                                c_void_p(y_dev.data_ptr()), y_host_slab.ctypes.data_as(c_void_p),
-                                               self.cuts.ctypes.data_as(POINTER(c_int64)), lo, hi, c_void_p(st)))
+                                               self.in_cuts_p(op), lo, hi, c_void_p(st)))
         return y_host_slab
 
     def cg(self, b, x, rtol=1e-10, maxit=200, hermitian=False, check_every=8, stream=None):
@@ -214,3 +230,24 @@ class SlabMatrix:
                                     self.cuts.ctypes.data_as(POINTER(c_int64)), byref(opt), byref(it), byref(rr),
                                     c_void_p(st)))
         return int(it.value), float(rr.value)
+
+
+class ColumnSplitMatrix:
+    """A matrix right-hand side sharded by COLUMNS: every rank holds A and its column group of X / Y — one plain
+    multi-RHS multiply per rank (spmm_tma_kernel), no exchange at all. This is how C5 (64 right-hand sides) runs on N
+    GPUs: row slabs would have to replicate all of X on every rank (512 MB per step)."""
+
+    def __init__(self, A, comm: Comm, nrhs: int, variant=L.VARIANT_AUTO):
+        self.comm, self.nrhs = comm, int(nrhs)
+        base, rem = divmod(self.nrhs, comm.nranks)
+        starts = [r * base + min(r, rem) for r in range(comm.nranks + 1)]
+        self.col_cuts = np.asarray(starts, np.int64)
+        self.cols = (int(starts[comm.rank]), int(starts[comm.rank + 1]))
+        self.local = DeviceMatrix(A, device=comm.device, variant=variant)
+        self.size, self.dtype = A.size, self.local.dtype
+
+    def mul(self, op, x_cols, y_cols=None, alpha=True, beta=False, stream=None):
+        """x_cols: this rank's column group (rows x (cols[1] - cols[0]), column-major CUDA tensor or host array)."""
+        if (1 if x_cols.ndim == 1 else x_cols.shape[1]) != self.cols[1] - self.cols[0]:
+            raise ValueError("DimensionMismatch: x must hold this rank's column group")
+        return self.local.mul(op, x_cols, y_cols, alpha, beta, stream)

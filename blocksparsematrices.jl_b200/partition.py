@@ -116,10 +116,13 @@ def _touches(idx, lo, hi) -> bool:
     return bool(np.any((idx > lo) & (idx <= hi)))       # 1-based values against the 0-based [lo, hi)
 
 
-def extract_slab(A, lo: int, hi: int, ops=("N",)):
+def extract_slab(A, lo: int, hi: int, ops=("N",), cols=None):
     """Host container holding exactly the blocks that contribute to outputs [lo, hi) of op(A) x for the
     given ops (block data is shared with A, nothing is copied). Sizes and index vectors are unchanged, so
-    x stays full length and the slab can be handed to DeviceMatrix(..., own_rows=(lo, hi), own_cols=(lo, hi))."""
+    x stays full length and the slab can be handed to DeviceMatrix(..., own_rows=(lo, hi), own_cols=(lo, hi)).
+    cols = (clo, chi): the output range of the transposed ops when it differs from the row range (non-square
+    operators: rows and columns are partitioned separately)."""
+    clo, chi = (lo, hi) if cols is None else (int(cols[0]), int(cols[1]))
     if isinstance(A, SymmetricBlockMatrix):
         dk = [i for i, idx in enumerate(A.diagonalindices) if _touches(idx, lo, hi)]
         ok = [i for i, (r, c) in enumerate(zip(A.rowindices, A.colindices))
@@ -135,7 +138,7 @@ def extract_slab(A, lo: int, hi: int, ops=("N",)):
                 m, n = A.blocks[b].shape
                 c0 = int(A.colindices[b])
                 if ("N" in ops and _touches((r0, m), lo, hi)) or \
-                        (("T" in ops or "C" in ops) and _touches((c0, n), lo, hi)):
+                        (("T" in ops or "C" in ops) and _touches((c0, n), clo, chi)):
                     keep.append(A.blocks[b])
                     rs.append(r0)
                     cs.append(c0)
@@ -143,6 +146,6 @@ def extract_slab(A, lo: int, hi: int, ops=("N",)):
             raise ValueError("empty slab: a VBCRS needs at least one block")
         return VariableBlockCompressedRowStorage(keep, rs, cs, A.size)
     k = [i for i, (r, c) in enumerate(zip(A.rowindices, A.colindices))
-         if ("N" in ops and _touches(r, lo, hi)) or (("T" in ops or "C" in ops) and _touches(c, lo, hi))]
+         if ("N" in ops and _touches(r, lo, hi)) or (("T" in ops or "C" in ops) and _touches(c, clo, chi))]
     return BlockSparseMatrix([A.blocks[i] for i in k], [A.rowindices[i] for i in k],
                              [A.colindices[i] for i in k], A.size)

@@ -140,6 +140,39 @@ def _worker(rank, world, port, q, quick=False):
         errs[("peer_host", "N")] = rel2(yh, 2 * ref)
         dist.barrier()
         comm.free(xs)
+        # non-square operator: rows and columns are partitioned separately (x of op N is sharded like the columns)
+        rngr = np.random.default_rng(12)
+        nr, nc = 3000, 5200
+        rb, rr, rc = [], [], []
+        for _ in range(300):
+            m, k = int(rngr.integers(1, 200)), int(rngr.integers(1, 200))
+            r0, c0 = int(rngr.integers(1, nr - m + 2)), int(rngr.integers(1, nc - k + 2))
+            rb.append(np.asfortranarray(rngr.standard_normal((m, k))))
+            rr.append(np.arange(r0, r0 + m, dtype=np.int64))
+            rc.append(np.arange(c0, c0 + k, dtype=np.int64))
+        R = B.BlockSparseMatrix(rb, rr, rc, (nr, nc))
+        SR = SlabMatrix(R, comm, ops=("N", "T"))
+        for op in ("N", "T"):
+            nin, nout = (nc, nr) if op == "N" else (nr, nc)
+            ilo, ihi = SR.own_cols if op == "N" else SR.own
+            olo, ohi = SR.out_range(op)
+            xt = rngr.standard_normal(nin)
+            ref = oracle_mul(R, xt, op)[olo:ohi]
+            xs = comm.alloc(nin, R.dtype)
+            xs.fill_(float("nan"))
+            xs[ilo:ihi] = torch.from_numpy(xt[ilo:ihi]).cuda()
+            yr = torch.zeros(nout, dtype=torch.float64, device="cuda")
+            SR.mul_peer(op, xs, yr)
+            torch.cuda.synchronize()
+            errs[("rect_peer", op)] = rel2(yr.cpu().numpy()[olo:ohi], ref)
+            xg = torch.full((nin,), float("nan"), dtype=torch.float64, device="cuda")
+            xg[ilo:ihi] = torch.from_numpy(xt[ilo:ihi]).cuda()
+            yr.zero_()
+            SR.mul(op, xg, yr)
+            torch.cuda.synchronize()
+            errs[("rect_nccl", op)] = rel2(yr.cpu().numpy()[olo:ohi], ref)
+            dist.barrier()
+            comm.free(xs)
         # solver loop on the sharded operator: COCG on a complex symmetric near-field matrix, the residual recomputed
         # with the oracle on the full matrix
         A = G.symmetric_nearfield(seed=61, n=20000, k_near=4, diag_shift=300.0 + 60.0j)
