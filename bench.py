@@ -562,9 +562,12 @@ def run_workload(cx, name, primary):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": spec["dtype"], "data": "synthetic",
         "gflops": work["flops"] / (ms_step * 1e-3) / 1e9,
-        "config": {"workload": spec["desc"], "op": op, "l2": "working set larger than L2 (no flush needed)"
-                   if not l2_resident else "working set fits L2: L2 flushed (256 MB write) before every timed iteration, "
-                                           "each multiply timed by its own CUDA events",
+        "config": {"workload": spec["desc"], "op": op,
+                   "l2": ("working set fits L2: L2 flushed (256 MB write) before every timed iteration, each multiply timed "
+                          "by its own CUDA events") if l2_resident else
+                         ("WARM L2 on request (--warm-l2): the working set fits L2 and is NOT flushed between iterations (the "
+                          "solver-loop case)" if (args.warm_l2 and work["bytes"] <= 4 * 126e6) else
+                          "working set larger than L2 (no flush needed)"),
                    "variant": {0: "auto", 1: "gather", 2: "fused", 3: "color", 4: "fused_tma"}[args.variant],
                    "parallelism": par, "algorithmic_bytes": work["bytes"], "flops": work["flops"],
                    "gen_s": round(t_gen, 1), "pack_s": round(t_pack, 1), "plan": stats},

@@ -741,10 +741,15 @@ __device__ __forceinline__ void tma_consumer(const MulArgs<T> &a, const bsm_slic
     for (int32_t ci = sl.c_begin; ci < sl.c_end; ++ci) {
         const bsm_contrib cb = a.contrib[ci];
         const SetRef in = set_ref(a, cb.in_set);
-        const int32_t m = cb.m;
-        const int32_t cc = chunk_cols<T>(m);
         const bool tform = (cb.form & 1) != 0;
         const bool fusedT = (cb.form & 2) != 0;
+        // GEN: a 256-row piece of a LONG N-form segment — the producer copies the rows [r0, r1) of every column as one
+        // piece each (16-byte aligned by construction), the pieces sit side by side with leading dimension `m`
+        const bool piece = GEN && !tform && (r0 > 0 || min(sl.r1, cb.out_len) < cb.m);
+        const int32_t prow = min(sl.r1, cb.out_len) - r0;
+        if (piece && prow <= 0) continue;
+        const int32_t m = piece ? (prow + (int32_t)(16 / sizeof(T)) - 1) / (int32_t)(16 / sizeof(T)) * (int32_t)(16 / sizeof(T)) : cb.m;
+        const int32_t cc = chunk_cols<T>(m);
         const int32_t jlo = tform ? r0 : 0;
         const int32_t jhi = tform ? min(sl.r1, cb.out_len) : cb.n;
         if (jhi <= jlo || m == 0) continue;
@@ -767,7 +772,7 @@ __device__ __forceinline__ void tma_consumer(const MulArgs<T> &a, const bsm_slic
             for (int32_t j0 = jw; j0 < wend; j0 += cc, ++q) {
                 const int32_t ncols = min(cc, wend - j0);
                 const uint32_t stage = q % kPStages;
-                const uint32_t delta = (uint32_t)(((int64_t)j0 * m * (int64_t)sizeof(T)) & 15);
+                const uint32_t delta = piece ? 0u : (uint32_t)(((int64_t)j0 * m * (int64_t)sizeof(T)) & 15);
                 mbar_wait(&full[stage], (q / kPStages) & 1);
                 const T *sm = reinterpret_cast<const T *>(stages + stage * kPStageBytes + delta);
                 if (GEN && tall)
@@ -812,9 +817,13 @@ __device__ __forceinline__ void tma_producer(const MulArgs<T> &a, const bsm_slic
     uint32_t q = 0;
     for (int32_t ci = sl.c_begin; ci < sl.c_end; ++ci) {
         const bsm_contrib cb = a.contrib[ci];
-        const int32_t m = cb.m;
-        const int32_t cc = chunk_cols<T>(m);
         const bool tform = (cb.form & 1) != 0;
+        const bool piece = !tform && (sl.r0 > 0 || min(sl.r1, cb.out_len) < cb.m);     // see tma_consumer (GEN plans only)
+        const int32_t prow = min(sl.r1, cb.out_len) - sl.r0;
+        if (piece && prow <= 0) continue;
+        constexpr int32_t kVec = (int32_t)(16 / sizeof(T));
+        const int32_t m = piece ? (prow + kVec - 1) / kVec * kVec : cb.m;
+        const int32_t cc = chunk_cols<T>(m);
         const int32_t jlo = tform ? sl.r0 : 0;
         const int32_t jhi = tform ? min(sl.r1, cb.out_len) : cb.n;
         if (jhi <= jlo || m == 0) continue;
@@ -825,6 +834,16 @@ __device__ __forceinline__ void tma_producer(const MulArgs<T> &a, const bsm_slic
                 const int32_t ncols = min(cc, wend - j0);
                 const uint32_t stage = q % kPStages;
                 if (q >= kPStages) mbar_wait(&empty[stage], ((q / kPStages) - 1) & 1);
+                if (piece) {
+                    // one copy per column: rows [r0, r0 + m) of column j0 + j (the packer only cuts such pieces when every
+                    // column of the block starts 16-byte aligned and r0 is a multiple of 256)
+                    const uint32_t pbytes = (uint32_t)m * (uint32_t)sizeof(T);
+                    mbar_arrive_expect_tx(&full[stage], pbytes * (uint32_t)ncols);
+                    for (int32_t j = 0; j < ncols; ++j)
+                        bulk_g2s(stages + stage * kPStageBytes + (size_t)j * pbytes,
+                                 blk + ((int64_t)(j0 + j) * cb.m + sl.r0) * (int64_t)sizeof(T), pbytes, &full[stage], policy);
+                    continue;
+                }
                 const int64_t boff = (int64_t)j0 * m * (int64_t)sizeof(T);
                 const uint32_t delta = (uint32_t)(boff & 15);
                 const uint32_t bytes = (delta + (uint32_t)ncols * (uint32_t)m * (uint32_t)sizeof(T) + 15u) & ~15u;

@@ -350,6 +350,32 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
             }
             continue;
         }
+        {
+            // long segment fed by N-form contributions only (1024-row blocks, op N): 256-row pieces through the CTA
+            // kernel — the producer copies the piece of every column with its own bulk copy, which needs every column of
+            // every block to start 16-byte aligned (m * s % 16 == 0; pieces start at multiples of 256 rows)
+            bool all_n = true, n_ok = true;
+            for (int64_t c = P.group_ptr[g]; c < P.group_ptr[g + 1]; ++c) {
+                if (P.contrib[c].form & kFormT) all_n = false;
+                if (((int64_t)P.contrib[c].m * s) % 16 != 0) n_ok = false;
+            }
+            if (pp.fused && L > kFusedMaxRows && all_n && n_ok && !any_fuse && entries > 0) {
+                for (int64_t r0 = 0; r0 < L; r0 += kFusedMaxRows) {
+                    Tmp t;
+                    t.s.out_set = gset[g];
+                    t.s.r0 = (int32_t)r0;
+                    t.s.r1 = (int32_t)std::min<int64_t>(L, r0 + kFusedMaxRows);
+                    t.s.c_begin = (int32_t)P.group_ptr[g];
+                    t.s.c_end = (int32_t)P.group_ptr[g + 1];
+                    t.s.flags = (P.group_direct[g] ? kSliceDirect : 0) | kSliceFused;
+                    t.s.scratch_off = 0;
+                    t.work = W * (t.s.r1 - t.s.r0) / L;
+                    t.order = (int64_t)tmp.size();
+                    tmp.push_back(t);
+                }
+                continue;
+            }
+        }
         int64_t pieces = (L + kMaxSliceHeight - 1) / kMaxSliceHeight;
         const int64_t by_work = (W + pp.work_target_bytes - 1) / pp.work_target_bytes;
         const int64_t max_pieces = std::max<int64_t>(1, L / hmin);

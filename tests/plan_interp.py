@@ -89,9 +89,15 @@ def run_plan(A, D, op, x, alpha=1.0, beta=0.0, beta_false=True, y=None, own=None
         fused = bool(s["flags"] & 4)
         assert 0 < h <= (256 if fused else 128)
         if fused and r0 > 0 or (fused and r1 < S.len[s["out_set"]]):
-            # column sub-range of a long segment: only T-form blocks of <= 1024 rows
-            assert all((contrib[ci]["form"] & 3) == 1 and contrib[ci]["m"] <= 1024
-                       for ci in range(s["c_begin"], s["c_end"]))
+            # sub-range of a long segment: either T-form blocks of <= 1024 rows only (a run of whole block columns), or
+            # N-form blocks only, cut into 256-row pieces whose columns all start 16-byte aligned
+            forms = {int(contrib[ci]["form"]) & 3 for ci in range(s["c_begin"], s["c_end"])}
+            assert forms in ({0}, {1}), forms
+            if forms == {1}:
+                assert all(contrib[ci]["m"] <= 1024 for ci in range(s["c_begin"], s["c_end"]))
+            else:
+                assert r0 % 256 == 0 and all((int(contrib[ci]["m"]) * D.dtype.itemsize) % 16 == 0
+                                             for ci in range(s["c_begin"], s["c_end"]))
         acc = np.zeros(h, dt)
         for ci in range(s["c_begin"], s["c_end"]):
             c = contrib[ci]

@@ -157,7 +157,8 @@ def test_c2_heavy_segments_split():
 def test_c2_tall_leaves_mix_fused_and_gather_kernels():
     A = G.symmetric_nearfield(seed=19, n=20000, leaf_min=150, leaf_max=400, k_near=3)
     sl = A.device().table(L.TAB_SLICE, 2)
-    assert 0 < ((sl["flags"] & 4) != 0).sum() < len(sl)
+    # leaves taller than 256 rows: 256-row pieces of long N-form segments through the CTA-stream kernel
+    assert np.any(((sl["flags"] & 4) != 0) & (sl["r0"] > 0))
     battery(A, reps=1)
 
 
