@@ -13,7 +13,8 @@ N > 1 (torchrun, one process per GPU):
   c2, c3   nnz-balanced block-row slabs, x kept sharded in peer-mapped arrays; the multiply kernels fetch the x
            entries they need from their owners over NVLink and carry both barriers themselves (no collective, no
            extra launch) — bsm_mul_dist_peer;
-  c5       the 64 right-hand sides are split across the ranks, A replicated (1.6 GB): no exchange at all.
+  c5       2-D grid of ranks: block-row slabs of A x column groups of the 64 right-hand sides (1 x 2, 2 x 2,
+           2 x 4 for N = 2, 4, 8: dist.rhs_grid), no exchange at all.
 "scaling": "strong" (the total work is fixed as N grows).
 
 ONE JSON line (rank 0). `value` = algorithmic GB/s with operands resident in HBM (CUDA events, max over ranks);
@@ -322,13 +323,18 @@ def run_workload(cx, name, primary):
     t_gen = time.time() - t0
     nin = A.size[1] if op == "N" else A.size[0]
     nout = A.size[0] if op == "N" else A.size[1]
-    rhs_split = world > 1 and nrhs > 1          # c5 on N GPUs: columns split, A replicated, no exchange
-    if rhs_split and nrhs % world:
-        raise SystemExit("the right-hand sides must divide evenly among the ranks")
+    rhs_split = world > 1 and nrhs > 1          # c5 on N GPUs: 2-D grid of row slabs x column groups, no exchange
+    GM = None
 
     t0 = time.time()
     SM = comm = None
-    if world > 1 and not rhs_split:
+    if rhs_split:
+        from bsm_b200.dist import GridSplitMatrix
+        grid = tuple(int(v) for v in args.rhs_grid.split("x")) if args.rhs_grid else None
+        GM = GridSplitMatrix(A, cx.comm, nrhs, op, grid, variant=args.variant)
+        D, own = GM.local, GM.out_rows
+        work = host_work(A, op, nrhs)
+    elif world > 1:
         from bsm_b200.dist import SlabMatrix
         comm = cx.comm
         if rb is None:        # generic partition of the full host matrix (every rank generated it)
@@ -346,7 +352,7 @@ def run_workload(cx, name, primary):
 
     # ---- operands: the same x on every arm and every rank
     xh = host_x(nin, nrhs, npdt)
-    j0, j1 = (rank * (nrhs // world), (rank + 1) * (nrhs // world)) if rhs_split else (0, nrhs)
+    j0, j1 = GM.cols if rhs_split else (0, nrhs)
     if nrhs == 1:
         x_full = torch.from_numpy(xh).to(dev)
         y_dev = torch.zeros(nout, dtype=tdt, device=dev)
@@ -451,11 +457,11 @@ def run_workload(cx, name, primary):
         yg = y_dev.t().cpu().numpy()
         num = den = 0.0
         for j in pc:
-            yo = orc(np.ascontiguousarray(xh[:, j]), op)
-            num += float(np.linalg.norm(yg[j - j0] - yo) ** 2)
+            yo = orc(np.ascontiguousarray(xh[:, j]), op)[own[0]:own[1]]
+            num += float(np.linalg.norm(yg[j - j0, own[0]:own[1]] - yo) ** 2)
             den += float(np.linalg.norm(yo) ** 2)
         err = float(np.sqrt(num / max(den, 1e-300)))
-        checked = f"columns {pc} of Y"
+        checked = f"columns {pc} of Y" + (f", rows {own[0]}:{own[1]}" if own != (0, nout) else "")
     del orc
     if world > 1:
         t = torch.tensor([err], device=dev, dtype=torch.float64)
@@ -477,7 +483,8 @@ def run_workload(cx, name, primary):
             xt, xa = pinned(xh[:, j0:j1].T)
             yt, ya = pinned(np.empty((j1 - j0, nout), npdt))
             run_e2e = lambda: D.mul(op, xa.T, ya.T)
-        h2d, d2h = nin * nrhs * npdt.itemsize, nout * nrhs * npdt.itemsize
+        # whole-job bytes: on a grid the R ranks of a column each copy that column group of X in
+        h2d, d2h = nin * nrhs * npdt.itemsize * (GM.grid[0] if GM is not None else 1), nout * nrhs * npdt.itemsize
     elif peer:
         xt, xa = pinned(xh[own[0]:own[1]])
         yt, ya = pinned(np.empty(own[1] - own[0], npdt))
@@ -514,6 +521,9 @@ def run_workload(cx, name, primary):
         solver = run_solver(cx, A, D, SM, own, host_threads)
 
     local_work = host_work(A, op, j1 - j0) if nrhs > 1 else host_work(A, op, 1)
+    if GM is not None and GM.grid[0] > 1:
+        lw = D.work(op, nrhs=j1 - j0)
+        local_work = {"bytes": lw["bytes"] - lw["index_table_bytes"], "flops": lw["flops"]}
     if SM is not None:      # this rank's slab: what its kernel streams
         lw = D.work(op, nrhs=1)
         local_work = {"bytes": lw["bytes"] - lw["index_table_bytes"], "flops": lw["flops"]}
@@ -551,7 +561,9 @@ def run_workload(cx, name, primary):
     if world == 1:
         par = "single GPU"
     elif rhs_split:
-        par = f"{nrhs} right-hand sides split x{world} ({nrhs // world} per rank), A replicated on every rank, no exchange"
+        R, C = GM.grid
+        par = (f"{R} x {C} grid: {R} block-row slab(s) of A x {C} column group(s) of the {nrhs} right-hand sides "
+               f"({nrhs // C} per rank), no exchange")
     elif peer:
         par = (f"block-row slabs x{world}, x sharded in peer-mapped arrays, fetched from its owners over NVLink inside "
                "the multiply kernels, both barriers inside the kernels (no collective, no extra launch)")
@@ -680,6 +692,8 @@ def main():
     ap.add_argument("--plan-hints", type=int, default=0, help="bsm_options.plan_hints (development)")
     ap.add_argument("--warm-l2", action="store_true", help="small workloads: do NOT flush L2 between the timed iterations "
                                                            "(the matrix stays L2-resident, as inside a solver loop); the line says so")
+    ap.add_argument("--rhs-grid", default="", help="c5 on N > 1: RxC grid of row slabs x column groups (default: the most "
+                                                   "square grid with C >= R)")
     ap.add_argument("--nrhs", type=int, default=0, help="c5: number of right-hand sides (development; default 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="default workload only: skip the c3 / c5 companion results")

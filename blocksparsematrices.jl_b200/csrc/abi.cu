@@ -74,7 +74,13 @@ struct DevPlan {
     DevBuf<bsm_wchunk> wchunk;
     DevBuf<int32_t> witem_ptr, mitem_ptr, muncovered;
     DevBuf<bsm_slice> mslices;
+    // row pieces of tall N-form blocks (CTA-stream kernel, real element types): tensor maps, built on first use
+    DevBuf<int32_t> contrib_map;
+    DevBuf<unsigned char> piece_maps;
+    int piece_state = 0;   // 0: not looked at, 1: maps in place, 2: the plan has no such pieces (or no tensor maps here)
     void release() {
+        contrib_map.release();
+        piece_maps.release();
         wchunk.release();
         witem_ptr.release();
         mitem_ptr.release();
@@ -107,6 +113,7 @@ struct bsm_matrix {
     // sparse(A) result built by bsm_sparse_build (sparse.cu), device arrays
     void *sparse_slot[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool restricted = false;
+    int64_t own_lo[2] = {0, 0}, own_hi[2] = {-1, -1};   // owned outputs of op N / op T, C (hi < 0: all)
     bool blocks_on_device = false;  // the block sources of the pending upload are device pointers
     int64_t plan_hints = 0;
     // tensor maps of the arena for spmm_tma_kernel (encoded on the first multi-RHS multiply)
@@ -345,6 +352,10 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
         pp[1].in_hi = opt->own_row_hi;
         A->variant = opt->variant;
         A->restricted = opt->own_row_hi >= 0 || opt->own_col_hi >= 0;
+        A->own_lo[0] = opt->own_row_lo;
+        A->own_hi[0] = opt->own_row_hi;
+        A->own_lo[1] = opt->own_col_lo;
+        A->own_hi[1] = opt->own_col_hi;
         A->blocks_on_device = opt->blocks_on_device != 0;
         A->plan_hints = opt->plan_hints;
     }
@@ -359,6 +370,8 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
     const int64_t split_div = tune_split ? std::max(1, std::atoi(tune_split)) : 8;
     const int64_t split = std::max<int64_t>(256 << 10, total_bytes / (148 * 2 * split_div));
     if (tune_witems) pp[0].witems_per_slot = pp[1].witems_per_slot = std::max(1, std::atoi(tune_witems));
+    if (const char *tune_wchunk = std::getenv("BSM_TUNE_WCHUNK"))   // fixed warp-stream chunk payload, 1024 .. 5120 bytes
+        pp[0].wchunk_bytes = pp[1].wchunk_bytes = std::min(5120, std::max(1024, std::atoi(tune_wchunk) / 16 * 16));
     std::string err = build_plan(H, ir[0], H.nrows, H.ncols, pp[0], H.plan[0]);
     if (err.empty()) err = build_plan(H, ir[1], H.ncols, H.nrows, pp[1], H.plan[1]);
     if (H.has_fused) {
@@ -493,14 +506,14 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 int encode_2d(CUtensorMap *map, CUtensorMapDataType dt, void *base, uint64_t d0, uint64_t d1, uint64_t stride1_bytes,
-              uint32_t b0, uint32_t b1) {
+              uint32_t b0, uint32_t b1, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail(BSM_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
     const cuuint64_t dims[2] = {d0, d1};
     const cuuint64_t strides[1] = {stride1_bytes};
     const cuuint32_t box[2] = {b0, b1};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    const CUresult r = fn(map, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(BSM_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
     return 0;
@@ -516,6 +529,55 @@ int ensure_arena_maps(bsm_matrix *A) {
                                (uint32_t)(TmaGeom<T>::ARows >> q)))
             return rc;
     A->tma_maps_ready = true;
+    return 0;
+}
+
+// Row pieces of tall N-form blocks in the CTA-stream plans (pack.cpp step 4, "long segment fed by N-form contributions
+// only"): per-column bulk copies of 1-2 KB run into the request rate of the copy engine (measured: 0.26 of the roofline
+// on the C4 matrix), so for Float32 / Float64 a piece of a whole chunk of columns is fetched as ONE box of a 2-D tensor
+// map. A map describes the arena as columns of m entries starting at the block's phase (offset mod m), so blocks of the
+// same height and phase share it; contributions beyond kMaxPieceMaps maps keep the per-column copies.
+constexpr size_t kMaxPieceMaps = 4096;
+template <class T>
+int ensure_piece_maps(bsm_matrix *A, const HostPlan &HP, DevPlan &DP) {
+    std::lock_guard<std::mutex> lk(A->tma_mu);
+    if (DP.piece_state) return 0;
+    DP.piece_state = 2;
+    if (sizeof(T) > 8 || !encode_tiled_fn()) return 0;
+    std::vector<int32_t> cmap(HP.contrib.size(), -1);
+    std::vector<std::pair<int64_t, int64_t>> keys;     // (m, phase in entries)
+    std::vector<CUtensorMap> maps;
+    const int64_t cc = kPChunk / (kFMaxRows * (int64_t)sizeof(T));
+    for (int64_t i = 0; i < HP.n_fused_slices; ++i) {
+        const bsm_slice &sl = HP.slices[(size_t)i];
+        for (int32_t c = sl.c_begin; c < sl.c_end; ++c) {
+            const bsm_contrib &cb = HP.contrib[(size_t)c];
+            if ((cb.form & kFormT) || cb.m == 0 || cb.n == 0 || cmap[(size_t)c] >= 0) continue;
+            if (!(sl.r0 > 0 || std::min<int32_t>(sl.r1, cb.out_len) < cb.m)) continue;
+            if (cb.m < kFMaxRows || ((int64_t)cb.m * sizeof(T)) % 16 != 0) continue;
+            const std::pair<int64_t, int64_t> key(cb.m, cb.off % cb.m);
+            size_t k = 0;
+            while (k < keys.size() && keys[k] != key) ++k;
+            if (k == keys.size()) {
+                if (keys.size() >= kMaxPieceMaps) continue;
+                const int64_t ncol = (A->H.arena_elems - key.second) / cb.m;
+                CUtensorMap tm;
+                if (int rc = encode_2d(&tm, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                                       (unsigned char *)A->arena + key.second * sizeof(T), (uint64_t)cb.m, (uint64_t)ncol,
+                                       (uint64_t)cb.m * sizeof(T), kFMaxRows, (uint32_t)cc, CU_TENSOR_MAP_SWIZZLE_NONE))
+                    return rc;
+                keys.push_back(key);
+                maps.push_back(tm);
+            }
+            cmap[(size_t)c] = (int32_t)k;
+        }
+    }
+    if (maps.empty()) return 0;
+    std::vector<unsigned char> raw(maps.size() * sizeof(CUtensorMap));
+    std::memcpy(raw.data(), maps.data(), raw.size());
+    if (int rc = DP.contrib_map.upload(cmap)) return rc;
+    if (int rc = DP.piece_maps.upload(raw)) return rc;
+    DP.piece_state = 1;
     return 0;
 }
 
@@ -609,6 +671,8 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
                void **scratch_io = nullptr, const PeerX *px = nullptr) {
     const int p = plan_index(A, op);
     const HostPlan &HP = A->H.plan[p];
+    if (HP.fused_general && HP.n_fused_slices > 0 && !A->plan[p].piece_state)
+        if (int rc = ensure_piece_maps<T>(A, HP, A->plan[p])) return rc;
     const DevPlan &DP = A->plan[p];
     T *scratch = nullptr;
     if (A->profiling && phase <= 1) {   // next slot of the event ring (one per multiply)
@@ -787,6 +851,10 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
         a.nslices = (int32_t)HP.slices.size();
         a.beta_false = beta_is_false ? 1 : 0;
         a.conj = (op == BSM_OP_C && sizeof(T) == 16) ? 1 : 0;
+        if (DP.piece_state == 1) {
+            a.contrib_map = DP.contrib_map.p;
+            a.piece_maps = DP.piece_maps.p;
+        }
         const bool prof = A->profiling && nrhs == 1;
         if (A->profiling && nrhs > 1 && j == 0) CUDA_TRY(cudaEventRecord(A->ev[0], st));
         if (prof) CUDA_TRY(cudaEventRecord(A->ev[0], st));
@@ -834,6 +902,9 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             w.cta_mode = HP.wcta ? 1 : 0;
             w.nz = 0;
             w.zrows = nullptr;
+            w.x_bulk_len = 0;
+            if (w.x.npeer == 0 && (reinterpret_cast<uintptr_t>(w.x.x) & 15) == 0)
+                w.x_bulk_len = (int32_t)(HP.in_dim / (16 / (int64_t)sizeof(T)) * (16 / (int64_t)sizeof(T)));
             if (fold_zero_rows) {   // single launch: the rows no block touches are set by extra CTAs of this kernel
                 w.nz = (int32_t)HP.gather_rows.size();
                 w.zrows = DP.gather_rows.p;
@@ -1351,14 +1422,21 @@ int bsm_mul_host(bsm_handle h, int op, const void *alpha, const void *beta, int 
         h->hy_bytes = yb;
     }
     cudaStream_t st = h->host_stream;
+    // slab handles (bsm_options.own_*): only the owned rows of y exist for this handle — they alone cross PCIe
+    const int ob = (op == BSM_OP_N) ? 0 : 1;
+    const int64_t olo = h->own_hi[ob] >= 0 ? std::max<int64_t>(0, h->own_lo[ob]) : 0;
+    const int64_t ohi = h->own_hi[ob] >= 0 ? std::min<int64_t>(nout, h->own_hi[ob]) : nout;
+    const size_t ypitch_h = (size_t)((nrhs > 1 ? ldy : nout) * s), ypitch_d = (size_t)(nout * s);
+    const size_t ywidth = (size_t)(std::max<int64_t>(0, ohi - olo) * s);
     CUDA_TRY(cudaMemcpy2DAsync(h->hx, (size_t)(nin * s), x_host, (size_t)((nrhs > 1 ? ldx : nin) * s),
                                (size_t)(nin * s), (size_t)nrhs, cudaMemcpyHostToDevice, st));
-    if (!beta_is_false)
-        CUDA_TRY(cudaMemcpy2DAsync(h->hy, (size_t)(nout * s), y_host, (size_t)((nrhs > 1 ? ldy : nout) * s),
-                                   (size_t)(nout * s), (size_t)nrhs, cudaMemcpyHostToDevice, st));
+    if (!beta_is_false && ywidth > 0)
+        CUDA_TRY(cudaMemcpy2DAsync((char *)h->hy + olo * s, ypitch_d, (const char *)y_host + olo * s, ypitch_h, ywidth,
+                                   (size_t)nrhs, cudaMemcpyHostToDevice, st));
     if (int rc = bsm_mul(h, op, alpha, beta, beta_is_false, h->hx, nin, h->hy, nout, nrhs, (void *)st)) return rc;
-    CUDA_TRY(cudaMemcpy2DAsync(y_host, (size_t)((nrhs > 1 ? ldy : nout) * s), h->hy, (size_t)(nout * s),
-                               (size_t)(nout * s), (size_t)nrhs, cudaMemcpyDeviceToHost, st));
+    if (ywidth > 0)
+        CUDA_TRY(cudaMemcpy2DAsync((char *)y_host + olo * s, ypitch_h, (const char *)h->hy + olo * s, ypitch_d, ywidth,
+                                   (size_t)nrhs, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
 }

@@ -250,6 +250,10 @@ struct MulArgs {
     int32_t nslices;
     int32_t beta_false;
     int32_t conj;
+    // GEN plans with row pieces of tall N-form blocks (real element types): contribution -> tensor map (-1: none), 128-byte
+    // CUtensorMap records in global memory (abi.cu: ensure_piece_maps)
+    const int32_t *contrib_map = nullptr;
+    const unsigned char *piece_maps = nullptr;
 };
 
 struct SetRef {
@@ -615,6 +619,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32
         ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
 }
+// global -> shared 2-D box through a tensor map (TMA tiled mode, SASS UTMALDG): the whole box counts towards the
+// barrier's transaction bytes, elements outside the tensor arrive as zeros
+__device__ __forceinline__ void tma_box_2d(void *dst_smem, const void *map, int32_t c0, int32_t c1, uint64_t *bar,
+                                           uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <class T>
@@ -748,7 +761,11 @@ __device__ __forceinline__ void tma_consumer(const MulArgs<T> &a, const bsm_slic
         const bool piece = GEN && !tform && (r0 > 0 || min(sl.r1, cb.out_len) < cb.m);
         const int32_t prow = min(sl.r1, cb.out_len) - r0;
         if (piece && prow <= 0) continue;
-        const int32_t m = piece ? (prow + (int32_t)(16 / sizeof(T)) - 1) / (int32_t)(16 / sizeof(T)) * (int32_t)(16 / sizeof(T)) : cb.m;
+        // real element types: the piece of a whole chunk of columns arrives as ONE tensor-map box of kFMaxRows rows (rows
+        // past the block are zero-filled, rows past the piece are never stored)
+        const bool boxed = piece && a.contrib_map != nullptr && __ldg(a.contrib_map + ci) >= 0;
+        const int32_t m = boxed ? kFMaxRows
+                          : piece ? (prow + (int32_t)(16 / sizeof(T)) - 1) / (int32_t)(16 / sizeof(T)) * (int32_t)(16 / sizeof(T)) : cb.m;
         const int32_t cc = chunk_cols<T>(m);
         const int32_t jlo = tform ? r0 : 0;
         const int32_t jhi = tform ? min(sl.r1, cb.out_len) : cb.n;
@@ -822,7 +839,9 @@ __device__ __forceinline__ void tma_producer(const MulArgs<T> &a, const bsm_slic
         const int32_t prow = min(sl.r1, cb.out_len) - sl.r0;
         if (piece && prow <= 0) continue;
         constexpr int32_t kVec = (int32_t)(16 / sizeof(T));
-        const int32_t m = piece ? (prow + kVec - 1) / kVec * kVec : cb.m;
+        const int32_t mapi = (piece && a.contrib_map != nullptr) ? __ldg(a.contrib_map + ci) : -1;
+        const bool boxed = mapi >= 0;
+        const int32_t m = boxed ? kFMaxRows : piece ? (prow + kVec - 1) / kVec * kVec : cb.m;
         const int32_t cc = chunk_cols<T>(m);
         const int32_t jlo = tform ? sl.r0 : 0;
         const int32_t jhi = tform ? min(sl.r1, cb.out_len) : cb.n;
@@ -834,6 +853,14 @@ __device__ __forceinline__ void tma_producer(const MulArgs<T> &a, const bsm_slic
                 const int32_t ncols = min(cc, wend - j0);
                 const uint32_t stage = q % kPStages;
                 if (q >= kPStages) mbar_wait(&empty[stage], ((q / kPStages) - 1) & 1);
+                if (boxed) {
+                    // the tensor map describes the arena as columns of cb.m entries starting at this block's phase: column
+                    // coordinate = (block offset) / cb.m + j0; the box is kFMaxRows x chunk_cols and always counts in full
+                    mbar_arrive_expect_tx(&full[stage], (uint32_t)(kFMaxRows * cc) * (uint32_t)sizeof(T));
+                    tma_box_2d(stages + stage * kPStageBytes, a.piece_maps + (size_t)mapi * 128, sl.r0,
+                               (int32_t)(cb.off / cb.m) + j0, &full[stage], policy);
+                    continue;
+                }
                 if (piece) {
                     // one copy per column: rows [r0, r0 + m) of column j0 + j (the packer only cuts such pieces when every
                     // column of the block starts 16-byte aligned and r0 is a multiple of 256)
@@ -947,6 +974,10 @@ struct WarpArgs {
     int32_t cta_mode;
     int32_t nz;
     const int32_t *zrows;
+    // x_bulk_len > 0: x is one local, 16-byte aligned array — the x values of a chunk (a contiguous range) are fetched by
+    // ONE bulk copy of the enclosing 16-byte aligned range, as long as that range ends at or before entry x_bulk_len
+    // (the length of x rounded down to whole 16-byte groups); 0: per-element copies (peer mode, unaligned x)
+    int32_t x_bulk_len;
 };
 
 struct WDesc {
@@ -1011,26 +1042,39 @@ __device__ __forceinline__ void wchunk_tform_dmma(const double *__restrict__ sm,
         c[t][0] = c[t][1] = 0.0;
         const int32_t j = 8 * t + g;
         jok[t] = j < nc;
+        // a column past the chunk reads column 0 instead: row g of the product is garbage and never stored, the other
+        // rows do not depend on it — no predicate and no zero fill in the loop
         ap[t] = sm + (jok[t] ? j : 0) * m + tg;
     }
-    const int32_t nfull = m >> 2;
-#pragma unroll 2
-    for (int32_t kt = 0; kt < nfull; ++kt) {
-        const double b = xin[4 * kt + tg];
+    const double *xp = xin + tg;
+    int32_t kt = m >> 2;
+    // 16 rows per trip: the fragment loads use immediate offsets, one pointer bump per column tile
+    for (; kt >= 4; kt -= 4) {
 #pragma unroll
-        for (int t = 0; t < NJT; ++t) {
-            double a = 0.0;
-            if (jok[t]) a = ap[t][4 * kt];
-            dmma_m8n8k4(c[t][0], c[t][1], a, b);
+        for (int u = 0; u < 4; ++u) {
+            const double b = xp[4 * u];
+#pragma unroll
+            for (int t = 0; t < NJT; ++t) dmma_m8n8k4(c[t][0], c[t][1], ap[t][4 * u], b);
         }
+        xp += 16;
+#pragma unroll
+        for (int t = 0; t < NJT; ++t) ap[t] += 16;
+    }
+    for (; kt > 0; --kt) {
+        const double b = *xp;
+#pragma unroll
+        for (int t = 0; t < NJT; ++t) dmma_m8n8k4(c[t][0], c[t][1], *ap[t], b);
+        xp += 4;
+#pragma unroll
+        for (int t = 0; t < NJT; ++t) ap[t] += 4;
     }
     if (m & 3) {
-        const bool rok = (4 * nfull + tg) < m;
-        const double b = rok ? xin[4 * nfull + tg] : 0.0;
+        // rows past the block: both operands zero (what lies behind the chunk in the ring need not be finite)
+        const bool rok = (m & ~3) + tg < m;
+        const double b = rok ? *xp : 0.0;
 #pragma unroll
         for (int t = 0; t < NJT; ++t) {
-            double a = 0.0;
-            if (rok && jok[t]) a = ap[t][4 * nfull];
+            const double a = rok ? *ap[t] : 0.0;
             dmma_m8n8k4(c[t][0], c[t][1], a, b);
         }
     }
@@ -1135,6 +1179,7 @@ __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned 
                                                  T *xs, T *ts, uint64_t *full, uint64_t *dbar, int32_t q0,
                                                  int32_t n) {
     const int lane = threadIdx.x & 31;
+    constexpr int32_t kXVec = (int32_t)(16 / sizeof(T));
     const uint64_t policy = l2_evict_first_policy();
     const int32_t nbatch = (n + kWDBatch - 1) / kWDBatch;
     auto load_batch = [&](int32_t b) {  // lane 0 only
@@ -1167,14 +1212,18 @@ __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned 
             uint64_t *bar = &full[ii & (kWNB - 1)];
             unsigned char *dst = ring + d.smem_off();
             const uint32_t bytes = d.bytes();
-            if (lane == 0) {
-                mbar_arrive_expect_tx(bar, bytes);
-                bulk_g2s(dst, a.arena + d.src_bytes(), bytes, bar, policy);
-            }
             const uint32_t fl = d.flags();
-            if (!(fl & 2u)) {
-                const int32_t cnt = (fl & 1u) ? d.m() : d.ncols();
-                const int32_t xr = d.x_ref();
+            const int32_t cnt = (fl & 1u) ? d.m() : d.ncols();
+            const int32_t xr = d.x_ref();
+            const int32_t xa0 = xr & ~(kXVec - 1), xa1 = (xr + cnt + kXVec - 1) & ~(kXVec - 1);
+            const bool xbulk = !(fl & 2u) && xa1 <= a.x_bulk_len;
+            if (lane == 0) {
+                const uint32_t xbytes = xbulk ? (uint32_t)(xa1 - xa0) * (uint32_t)sizeof(T) : 0u;
+                mbar_arrive_expect_tx(bar, bytes + xbytes);
+                bulk_g2s(dst, a.arena + d.src_bytes(), bytes, bar, policy);
+                if (xbulk) bulk_g2s_plain(dst + bytes, a.x.x + xa0, xbytes, bar);   // x is re-read: no evict-first hint
+            }
+            if (!(fl & 2u) && !xbulk) {
                 T *xd = reinterpret_cast<T *>(dst + bytes);
                 if (lane < cnt) cp_async_elem<(int)sizeof(T)>(xd + lane, a.x.ptr(xr + lane));
                 if (lane + 32 < cnt) cp_async_elem<(int)sizeof(T)>(xd + lane + 32, a.x.ptr(xr + lane + 32));
@@ -1203,6 +1252,10 @@ __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned 
         const bool tform = FORM == 2 ? (fl & 1u) != 0 : FORM == 1;
         const unsigned char *cbase = ring + d0.smem_off();
         const T *xin = reinterpret_cast<const T *>(cbase + d0.bytes());
+        {   // bulk-fetched x values start at the 16-byte group below x_ref (same test as in issue_ready)
+            const int32_t xr = d0.x_ref(), cnt = (fl & 1u) ? m : nc;
+            if (!(fl & 2u) && ((xr + cnt + kXVec - 1) & ~(kXVec - 1)) <= a.x_bulk_len) xin += xr & (kXVec - 1);
+        }
         if (fl & 8u) {  // first chunk of a segment
             acc0 = El<T>::zero();
             acc1 = El<T>::zero();

@@ -87,6 +87,33 @@ void layout_arena(HostMatrix &M) {
 }
 
 // ---------------------------------------------------------------------------- plan
+// Columns per chunk of a warp-stream contribution (m x n block, element size s). The per-chunk instruction cost of
+// stream_warp_kernel is fixed (descriptor, barrier, issue: ~1 us of a warp's time — measured on C3: time = a + b * chunks
+// with b = 0.38 ns (op N) / 0.63 ns (op T) per chunk), so chunks are as large as the ring allows with TWO of them
+// resident (one in flight while one is consumed): payload + its x values <= half the ring. T-form chunks prefer a
+// multiple of 8 columns (whole tensor-core tiles).
+static int64_t wchunk_cols(int64_t m, int64_t n, bool tform, int64_t s, int64_t tuned_bytes) {
+    const int64_t colbytes = m * s;
+    int64_t cmax;
+    if (tuned_bytes > 0) {
+        cmax = tuned_bytes / colbytes;
+    } else {
+        const int64_t half = kWRingBytes / 2 - 64;       // 16-byte alignment shifts and round-ups of both parts
+        cmax = tform ? (half - ((m * s + 15) & ~(int64_t)15)) / colbytes : half / (colbytes + s);
+    }
+    cmax = std::max<int64_t>(1, std::min<int64_t>(cmax, kWMaxCols));
+    const int64_t nch = (n + cmax - 1) / cmax;
+    int64_t cc = (n + nch - 1) / nch;
+    const int64_t c8 = (cc + 7) / 8 * 8, c4 = (cc + 3) / 4 * 4;
+    if (tform && c8 <= cmax)
+        cc = c8;
+    else if (c4 <= cmax)
+        cc = c4;
+    else
+        cc = cmax >= 4 ? cmax / 4 * 4 : cmax;
+    return std::max<int64_t>(cc, 1);
+}
+
 std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t out_dim,
                        int64_t in_dim, const PlanParams &pp, HostPlan &P) {
     IndexSets &S = M.sets;
@@ -360,18 +387,37 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
                 if (((int64_t)P.contrib[c].m * s) % 16 != 0) n_ok = false;
             }
             if (pp.fused && L > kFusedMaxRows && all_n && n_ok && !any_fuse && entries > 0) {
+                // a piece far heavier than the work-item budget is cut along the contribution list as well (the first
+                // item stays direct, the others deliver partial vectors through the gather lists)
+                const int64_t budget = pp.split_bytes > 0 ? pp.split_bytes : (int64_t)1 << 62;
                 for (int64_t r0 = 0; r0 < L; r0 += kFusedMaxRows) {
-                    Tmp t;
-                    t.s.out_set = gset[g];
-                    t.s.r0 = (int32_t)r0;
-                    t.s.r1 = (int32_t)std::min<int64_t>(L, r0 + kFusedMaxRows);
-                    t.s.c_begin = (int32_t)P.group_ptr[g];
-                    t.s.c_end = (int32_t)P.group_ptr[g + 1];
-                    t.s.flags = (P.group_direct[g] ? kSliceDirect : 0) | kSliceFused;
-                    t.s.scratch_off = 0;
-                    t.work = W * (t.s.r1 - t.s.r0) / L;
-                    t.order = (int64_t)tmp.size();
-                    tmp.push_back(t);
+                    const int64_t r1 = std::min<int64_t>(L, r0 + kFusedMaxRows);
+                    int32_t cb0 = (int32_t)P.group_ptr[g];
+                    const int32_t cend = (int32_t)P.group_ptr[g + 1];
+                    bool first_item = true;
+                    while (cb0 < cend) {
+                        int32_t ce = cb0;
+                        int64_t wk = 0;
+                        while (ce < cend) {
+                            const int64_t wc = (int64_t)P.contrib[ce].n * (r1 - r0) * s;
+                            if (ce > cb0 && wk + wc > budget + budget / 2) break;
+                            wk += wc;
+                            ++ce;
+                        }
+                        Tmp t;
+                        t.s.out_set = gset[g];
+                        t.s.r0 = (int32_t)r0;
+                        t.s.r1 = (int32_t)r1;
+                        t.s.c_begin = cb0;
+                        t.s.c_end = ce;
+                        t.s.flags = ((P.group_direct[g] && first_item) ? kSliceDirect : 0) | kSliceFused;
+                        t.s.scratch_off = 0;
+                        t.work = wk;
+                        t.order = (int64_t)tmp.size();
+                        tmp.push_back(t);
+                        first_item = false;
+                        cb0 = ce;
+                    }
                 }
                 continue;
             }
@@ -522,7 +568,9 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
                 int64_t c = 0;
                 for (int32_t k = t.s.c_begin; k < t.s.c_end; ++k) {
                     const int64_t bytes = (int64_t)P.contrib[k].m * P.contrib[k].n * s;
-                    c += bytes + 1024 * std::max<int64_t>((bytes + kWChunkBytes - 1) / kWChunkBytes, (P.contrib[k].n + kWMaxCols - 1) / kWMaxCols);
+                    if (bytes == 0) continue;
+                    const int64_t cc = wchunk_cols(P.contrib[k].m, P.contrib[k].n, (P.contrib[k].form & kFormT) != 0, s, pp.wchunk_bytes);
+                    c += bytes + 1024 * ((P.contrib[k].n + cc - 1) / cc);
                 }
                 return c;
             };
@@ -615,12 +663,7 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
                 if (cb.m == 0 || cb.n == 0) continue;
                 const bool tf = (cb.form & kFormT) != 0;
                 const int64_t colbytes = (int64_t)cb.m * s;
-                int64_t nch = ((int64_t)cb.n * colbytes + kWChunkBytes - 1) / kWChunkBytes;
-                nch = std::max<int64_t>(nch, (cb.n + kWMaxCols - 1) / kWMaxCols);
-                int64_t cc = (cb.n + nch - 1) / nch;
-                cc = (cc + 3) / 4 * 4;
-                cc = std::min<int64_t>(cc, std::min<int64_t>(kWMaxCols, kWChunkBytes / colbytes));
-                cc = std::max<int64_t>(cc / 4 * 4, 1);
+                const int64_t cc = wchunk_cols(cb.m, cb.n, tf, s, pp.wchunk_bytes);
                 for (int64_t j0 = 0; j0 < cb.n; j0 += cc) {
                     const int64_t nc = std::min<int64_t>(cc, cb.n - j0);
                     const int64_t b0 = cb.off * s + j0 * colbytes;      // first byte of the chunk
@@ -725,7 +768,8 @@ std::string build_plan(HostMatrix &M, const std::vector<ContribIR> &ir, int64_t 
             for (int32_t q = q0; q < q1; ++q) {
                 bsm_wchunk &w = P.wchunk[(size_t)q];
                 const int64_t cnt = (w.flags & kWcT) ? w.m : w.ncols;
-                const int64_t foot = (int64_t)w.bytes16 * 16 + ((cnt * s + 15) & ~(int64_t)15);
+                // x values behind the chunk: a bulk copy fetches the enclosing 16-byte aligned range (one more group)
+                const int64_t foot = (int64_t)w.bytes16 * 16 + ((cnt * s + 15) & ~(int64_t)15) + (s < 16 ? 16 : 0);
                 if (foot > kWRingBytes) return "warp-stream chunk larger than the ring";
                 for (;;) {
                     // live region: from the oldest live chunk's offset to head (circular)

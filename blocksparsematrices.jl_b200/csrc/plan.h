@@ -37,7 +37,7 @@ constexpr int kSliceWarp = 8;           // handled by stream_warp_kernel (whole 
 constexpr int kFusedMaxRows = 256;
 constexpr int kFusedMaxTRows = 1024;    // tallest T-form block the CTA kernel stages (x window in shared memory)
 constexpr int kWarpMaxRows = 64;        // segment length and block height limit of the warp-stream kernel
-constexpr int kWChunkBytes = 4096;      // largest block payload of one warp-stream chunk
+constexpr int kWChunkBytes = 4096;      // round-1 payload limit of a warp-stream chunk (plan_hints bit 2 / BSM_TUNE_WCHUNK)
 constexpr int kWRingBytes = 11264;      // shared-memory byte ring of one warp (chunks + their x values)
 constexpr int kWSlots = 16;             // mbarrier slots of one warp: chunks in flight + the one being consumed
 constexpr int kWMaxCols = 64;           // columns per warp-stream chunk (two prefetched x values per lane)
@@ -168,6 +168,7 @@ struct PlanParams {
                                        // through the gather lists) to expose enough parallelism; 0: off
     int64_t witem_bytes = 0;           // target bytes per warp work item (0: derived from the total)
     int64_t witems_per_slot = 0;       // warp work items per resident warp slot (0: automatic)
+    int64_t wchunk_bytes = 0;          // largest warp-stream chunk payload; 0: as much as lets two chunks share the ring
     bool wcta = true;                  // small problems with few segments may use the CTA-part mode (HostPlan::wcta)
 };
 

@@ -232,22 +232,63 @@ class SlabMatrix:
         return int(it.value), float(rr.value)
 
 
-class ColumnSplitMatrix:
-    """A matrix right-hand side sharded by COLUMNS: every rank holds A and its column group of X / Y — one plain
-    multi-RHS multiply per rank (spmm_tma_kernel), no exchange at all. This is how C5 (64 right-hand sides) runs on N
-    GPUs: row slabs would have to replicate all of X on every rank (512 MB per step)."""
+def rhs_grid(nranks: int, nrhs: int):
+    """(row groups R, column groups C), R * C == nranks, for a matrix right-hand side on `nranks` GPUs: the most square
+    grid with C >= R whose column groups divide the right-hand sides evenly. More column groups = less of X on every rank
+    (and over PCIe); more row groups = less of A streamed per rank."""
+    best = (1, nranks)
+    for r in range(1, nranks + 1):
+        if nranks % r == 0 and r <= nranks // r and nrhs % (nranks // r) == 0:
+            best = (r, nranks // r)
+    if nrhs % best[1]:
+        raise ValueError("the right-hand sides must divide evenly among the column groups")
+    return best
+
+
+class GridSplitMatrix:
+    """A matrix right-hand side on a 2-D grid of ranks, no exchange at all: rank i*C + j holds the block rows of slab i
+    (balanced by streamed bytes, partition.slab_cuts) and multiplies them with column group j of X, writing rows
+    out_rows of column group j of Y — one plain multi-RHS multiply per rank (spmm_tma_kernel). R = 1 is the pure column
+    split (A replicated); row slabs alone (C = 1) would need all of X on every rank (512 MB per step for C5). The R ranks
+    of a column hold the same column group of X."""
+
+    def __init__(self, A, comm: Comm, nrhs: int, op="N", grid=None, variant=L.VARIANT_AUTO):
+        self.comm, self.nrhs, self.op = comm, int(nrhs), op
+        self.grid = R, C = tuple(grid) if grid is not None else rhs_grid(comm.nranks, self.nrhs)
+        if R * C != comm.nranks or self.nrhs % C:
+            raise ValueError("grid must have nranks entries and its column groups must divide nrhs")
+        i, j = divmod(comm.rank, C)
+        per = self.nrhs // C
+        self.cols = (j * per, (j + 1) * per)
+        nout = A.size[0] if op == "N" else A.size[1]
+        self.size = A.size
+        if R == 1:
+            self.out_rows = (0, nout)
+            self.local = DeviceMatrix(A, device=comm.device, variant=variant)
+        else:
+            cuts = slab_cuts(A, R, op)
+            lo, hi = int(cuts[i]), int(cuts[i + 1])
+            self.out_rows = (lo, hi)
+            S = extract_slab(A, lo, hi, (op,), cols=(lo, hi))
+            own = dict(own_rows=(lo, hi)) if op == "N" else dict(own_cols=(lo, hi))
+            self.local = DeviceMatrix(S, device=comm.device, variant=variant, **own)
+        self.dtype = self.local.dtype
+
+    def mul(self, x_cols, y_cols=None, alpha=True, beta=False, stream=None):
+        """x_cols: this rank's column group of X (rows x (cols[1] - cols[0]), column-major CUDA tensor or host array);
+        rows out_rows of y_cols are written, the others are left alone."""
+        if (1 if x_cols.ndim == 1 else x_cols.shape[1]) != self.cols[1] - self.cols[0]:
+            raise ValueError("DimensionMismatch: x must hold this rank's column group")
+        return self.local.mul(self.op, x_cols, y_cols, alpha, beta, stream)
+
+
+class ColumnSplitMatrix(GridSplitMatrix):
+    """The R = 1 grid: every rank holds A and its column group of X / Y."""
 
     def __init__(self, A, comm: Comm, nrhs: int, variant=L.VARIANT_AUTO):
-        self.comm, self.nrhs = comm, int(nrhs)
-        base, rem = divmod(self.nrhs, comm.nranks)
-        starts = [r * base + min(r, rem) for r in range(comm.nranks + 1)]
-        self.col_cuts = np.asarray(starts, np.int64)
-        self.cols = (int(starts[comm.rank]), int(starts[comm.rank + 1]))
-        self.local = DeviceMatrix(A, device=comm.device, variant=variant)
-        self.size, self.dtype = A.size, self.local.dtype
+        super().__init__(A, comm, nrhs, "N", (1, comm.nranks), variant)
 
     def mul(self, op, x_cols, y_cols=None, alpha=True, beta=False, stream=None):
-        """x_cols: this rank's column group (rows x (cols[1] - cols[0]), column-major CUDA tensor or host array)."""
         if (1 if x_cols.ndim == 1 else x_cols.shape[1]) != self.cols[1] - self.cols[0]:
             raise ValueError("DimensionMismatch: x must hold this rank's column group")
         return self.local.mul(op, x_cols, y_cols, alpha, beta, stream)

@@ -150,7 +150,8 @@ int bsm_mul(bsm_handle h, int op, const void *alpha, const void *beta, int beta_
             const void *x_dev, int64_t ldx, void *y_dev, int64_t ldy, int64_t nrhs, void *stream);
 
 /* Same with HOST x / y (pageable or pinned): H2D of x (and of y when beta is used) into device buffers owned by
- * the handle, multiply, D2H of y, then synchronises (serialised per handle). */
+ * the handle, multiply, D2H of y, then synchronises (serialised per handle). Slab handles (bsm_options.own_*): only the
+ * owned rows of y are read and written, the other rows of y_host are left alone. */
 int bsm_mul_host(bsm_handle h, int op, const void *alpha, const void *beta, int beta_is_false,
                  const void *x_host, int64_t ldx, void *y_host, int64_t ldy, int64_t nrhs);
 

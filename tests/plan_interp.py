@@ -199,7 +199,9 @@ def run_warp_stream(D, plan, arena, S, slices, x_full, x_local, y, scratch, writ
             assert 0 < m <= 64 and 0 < nc <= 64 and Lseg <= 64
             src = ((int(c["src16_hi"]) << 32) | int(c["src16"])) * 16
             nbytes = int(c["bytes16"]) * 16
-            assert nbytes <= 4096 + 16 and int(c["delta"]) + m * nc * isz <= nbytes
+            # a chunk and its x values take at most half the ring: the next chunk is in flight while this one is consumed
+            assert nbytes + (((m if (fl & 1) else nc) * isz + 15) & ~15) + (16 if isz < 16 else 0) <= RING_BYTES // 2
+            assert int(c["delta"]) + m * nc * isz <= nbytes
             buf = raw[src:src + nbytes]
             Bc = buf[int(c["delta"]):int(c["delta"]) + m * nc * isz].view(arena.dtype).reshape((m, nc), order="F")
             if conj:
@@ -262,7 +264,7 @@ def check_ring_schedule(ch, isz):
     n = len(ch)
     foot = ch["bytes16"].astype(np.int64) * 16
     cnt = np.where(ch["flags"] & 1, ch["m"], ch["ncols"]).astype(np.int64)
-    foot += (cnt * isz + 15) // 16 * 16
+    foot += (cnt * isz + 15) // 16 * 16 + (16 if isz < 16 else 0)     # x values: the enclosing 16-byte aligned range
     off = ch["smem16"].astype(np.int64) * 16
     assert np.all(off + foot <= RING_BYTES)
     lag = ch["lag"].astype(np.int64)

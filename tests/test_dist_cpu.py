@@ -156,3 +156,11 @@ def test_non_square_operator_slabs_rows_and_columns_cut_separately():
             full[own[0]:own[1]] = y[own[0]:own[1]]
         ref = oracle_mul(A, x, op)
         assert np.linalg.norm(full - ref) / np.linalg.norm(ref) < 1e-13, op
+
+
+def test_rhs_grid_prefers_column_groups_and_divides_the_right_hand_sides():
+    from bsm_b200.dist import rhs_grid
+    assert [rhs_grid(n, 64) for n in (1, 2, 4, 8)] == [(1, 1), (1, 2), (2, 2), (2, 4)]
+    assert rhs_grid(8, 4) == (2, 4) and rhs_grid(4, 2) == (2, 2) and rhs_grid(6, 9) == (2, 3)
+    with pytest.raises(ValueError):
+        rhs_grid(4, 3)        # no grid whose column groups divide 3 right-hand sides

@@ -173,6 +173,34 @@ def _worker(rank, world, port, q, quick=False):
             errs[("rect_nccl", op)] = rel2(yr.cpu().numpy()[olo:ohi], ref)
             dist.barrier()
             comm.free(xs)
+        # matrix right-hand side on a grid of ranks (no exchange): 1 x 2 = column groups with A replicated, 2 x 1 = row
+        # slabs with the same X on both ranks; device tensors and the host-pointer call (which moves the owned rows only)
+        from bsm_b200.dist import GridSplitMatrix, rhs_grid
+        assert rhs_grid(2, 16) == (1, 2) and rhs_grid(4, 64) == (2, 2) and rhs_grid(8, 64) == (2, 4)
+        Ag = G.blocksparse_uniform(seed=57, n=9600, nblocks=2500, bs=32)
+        Xg = np.asfortranarray(np.random.default_rng(58).standard_normal((9600, 16)))
+        for op in ("N", "T"):
+            Yref = np.stack([oracle_mul(Ag, np.ascontiguousarray(Xg[:, j]), op) for j in range(16)], axis=1)
+            for grid in ((1, 2), (2, 1)):
+                GM = GridSplitMatrix(Ag, comm, 16, op, grid)
+                j0, j1 = GM.cols
+                lo, hi = GM.out_rows
+                xd = torch.from_numpy(np.ascontiguousarray(Xg[:, j0:j1].T)).cuda().t()
+                yd = torch.full((j1 - j0, 9600), float("nan"), dtype=torch.float64, device="cuda").t()
+                GM.mul(xd, yd)
+                torch.cuda.synchronize()
+                yh = yd.cpu().numpy()
+                errs[("grid%dx%d" % grid, op)] = rel2(yh[lo:hi], Yref[lo:hi, j0:j1])
+                if grid[0] > 1:      # rows of the other slab are left alone
+                    other = np.ones(9600, bool)
+                    other[lo:hi] = False
+                    assert np.all(np.isnan(yh[other]))
+                yhost = np.full((9600, j1 - j0), np.nan, order="F")
+                GM.mul(np.asfortranarray(Xg[:, j0:j1]), yhost)
+                errs[("grid%dx%d_host" % grid, op)] = rel2(yhost[lo:hi], Yref[lo:hi, j0:j1])
+                if grid[0] > 1:
+                    assert np.all(np.isnan(yhost[other]))
+                dist.barrier()
         # solver loop on the sharded operator: COCG on a complex symmetric near-field matrix, the residual recomputed
         # with the oracle on the full matrix
         A = G.symmetric_nearfield(seed=61, n=20000, k_near=4, diag_shift=300.0 + 60.0j)

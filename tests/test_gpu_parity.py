@@ -163,6 +163,24 @@ def test_c2_tall_leaves_mix_fused_and_gather_kernels():
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
+def test_tall_n_form_pieces_through_tensor_map_boxes(dtype):
+    # long all-N-form segments: 256-row pieces; Float32 / Float64 fetch a piece of a chunk of columns as ONE tensor-map
+    # box (blocks of two heights and several phases share maps, the last piece is shorter than the box), ComplexF64 keeps
+    # the per-column copies
+    from test_packing_cpu import tall_shared_rows_bsm
+    blocks, rows, cols, size = tall_shared_rows_bsm(np.random.default_rng(41), np.float64)
+    if np.dtype(dtype).kind == "c":
+        rng = np.random.default_rng(5)
+        blocks = [np.asfortranarray(b + 1j * rng.standard_normal(b.shape)) for b in blocks]
+    else:
+        blocks = [np.asfortranarray(b.astype(dtype)) for b in blocks]
+    A = B.BlockSparseMatrix(blocks, rows, cols, size)
+    sl = A.device().table(L.TAB_SLICE, 2)
+    assert np.any(((sl["flags"] & 4) != 0) & (sl["r0"] > 0))
+    battery(A, reps=1)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex128])
 def test_c3_shape(dtype):
     A = G.vbcrs_variable(seed=13, n=60000, dtype=dtype)
     battery(A, reps=1)

@@ -162,6 +162,38 @@ def test_tall_and_wide_blocks_are_sliced():
     assert np.all(sl["r1"] - sl["r0"] <= 128) and len(sl) >= 4
 
 
+def tall_shared_rows_bsm(rng, dtype=np.float64):
+    """Four tall blocks on ONE 700-row index set (plus one on a 520-row set and a short one): op N feeds long all-N-form
+    segments, cut into 256-row pieces of the CTA-stream kernel and, being heavy, along the contribution list too."""
+    mk = lambda m, n: np.asfortranarray(rng.standard_normal((m, n)).astype(dtype))
+    blocks = [mk(700, 300), mk(700, 210), mk(700, 44), mk(700, 260), mk(520, 300), mk(30, 50)]
+    r700, r520 = np.arange(1, 701), np.arange(701, 1221)
+    rows = [r700, r700, r700, r700, r520, np.arange(1221, 1251)]
+    cols = [np.arange(1, 301), np.arange(301, 511), np.arange(511, 555), np.arange(600, 860), np.arange(11, 311),
+            np.arange(1, 51)]
+    return blocks, rows, cols, (1250, 900)
+
+
+def test_tall_n_form_pieces_are_cut_along_the_contribution_list():
+    rng = np.random.default_rng(41)
+    blocks, rows, cols, size = tall_shared_rows_bsm(rng)
+    A = O.OBSM(blocks, rows, cols, size)
+    P = B.BlockSparseMatrix(blocks, rows, cols, size)
+    D = host_only(P)
+    for op in OPS:
+        x = rng.standard_normal(size[1] if op == "N" else size[0])
+        assert rel(run_plan(P, D, op, x), O.mul_bsm(A, x, op)) < 1e-13
+        y0 = rng.standard_normal(size[0] if op == "N" else size[1])
+        assert rel(run_plan(P, D, op, x, 0.5, -1.5, False, y0.copy()), O.mul_bsm(A, x, op, 0.5, -1.5, False, y0.copy())) < 1e-13
+    sl = D.table(L.TAB_SLICE, 2)      # stream plan of op N
+    fused = (sl["flags"] & 4) != 0
+    pieces = sl[fused & (sl["r1"] - sl["r0"] <= 256) & (sl["r1"] > 256)]
+    assert len(pieces) >= 4, "expected 256-row pieces of the long N-form segments"
+    # 256 x 300 x 8 bytes per contribution and piece is above the work-item budget: the partial items are not direct
+    assert np.any((pieces["flags"] & 1) == 0) and np.any((pieces["flags"] & 1) != 0)
+    assert np.any(pieces["c_end"] - pieces["c_begin"] == 1)
+
+
 def test_clean_vbcrs_is_single_launch():
     rng = np.random.default_rng(8)
     tiles = np.cumsum(np.r_[1, rng.integers(3, 9, 12)])
