@@ -903,8 +903,11 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             w.nz = 0;
             w.zrows = nullptr;
             w.x_bulk_len = 0;
-            if (w.x.npeer == 0 && (reinterpret_cast<uintptr_t>(w.x.x) & 15) == 0)
-                w.x_bulk_len = (int32_t)(HP.in_dim / (16 / (int64_t)sizeof(T)) * (16 / (int64_t)sizeof(T)));
+            {
+                bool aligned = (reinterpret_cast<uintptr_t>(w.x.x) & 15) == 0;
+                for (int r = 0; r < w.x.npeer; ++r) aligned = aligned && (reinterpret_cast<uintptr_t>(w.x.peer[r]) & 15) == 0;
+                if (aligned) w.x_bulk_len = (int32_t)(HP.in_dim / (16 / (int64_t)sizeof(T)) * (16 / (int64_t)sizeof(T)));
+            }
             if (fold_zero_rows) {   // single launch: the rows no block touches are set by extra CTAs of this kernel
                 w.nz = (int32_t)HP.gather_rows.size();
                 w.zrows = DP.gather_rows.p;
@@ -913,14 +916,14 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
                 w.x.sync.do_exit = 1;
                 w.x.sync.arrivals = (int32_t)((w.nitems + kWWarps - 1) / kWWarps) * kWWarps;
             }
-            const unsigned zctas = (unsigned)((w.nz + kWWarps * 32 - 1) / (kWWarps * 32));
+            const unsigned zctas = (unsigned)((w.nz + kWThreads - 1) / kWThreads);
             const unsigned wgrid = (unsigned)((w.nitems + kWWarps - 1) / kWWarps) + zctas;
             if (HP.wform == 0)
-                stream_warp_kernel<T, 0><<<wgrid, kWWarps * 32, stream_warp_smem_bytes<T>(), st>>>(w);
+                stream_warp_kernel<T, 0><<<wgrid, kWThreads, stream_warp_smem_bytes<T>(), st>>>(w);
             else if (HP.wform == 1)
-                stream_warp_kernel<T, 1><<<wgrid, kWWarps * 32, stream_warp_smem_bytes<T>(), st>>>(w);
+                stream_warp_kernel<T, 1><<<wgrid, kWThreads, stream_warp_smem_bytes<T>(), st>>>(w);
             else
-                stream_warp_kernel<T, 2><<<wgrid, kWWarps * 32, stream_warp_smem_bytes<T>(), st>>>(w);
+                stream_warp_kernel<T, 2><<<wgrid, kWThreads, stream_warp_smem_bytes<T>(), st>>>(w);
             CUDA_TRY(cudaGetLastError());
         }
         if (g1 > g0) {

@@ -974,9 +974,9 @@ struct WarpArgs {
     int32_t cta_mode;
     int32_t nz;
     const int32_t *zrows;
-    // x_bulk_len > 0: x is one local, 16-byte aligned array — the x values of a chunk (a contiguous range) are fetched by
-    // ONE bulk copy of the enclosing 16-byte aligned range, as long as that range ends at or before entry x_bulk_len
-    // (the length of x rounded down to whole 16-byte groups); 0: per-element copies (peer mode, unaligned x)
+    // x_bulk_len > 0: x (peer mode: every owner's array) is 16-byte aligned — the x values of a chunk (a contiguous range)
+    // are fetched by ONE bulk copy of the enclosing 16-byte aligned range, as long as that range ends at or before entry
+    // x_bulk_len (the length of x rounded down to whole 16-byte groups); 0: per-element copies (unaligned x)
     int32_t x_bulk_len;
 };
 
@@ -1087,15 +1087,17 @@ __device__ __forceinline__ void wchunk_tform_dmma(const double *__restrict__ sm,
 
 __device__ __forceinline__ void wchunk_tform_dmma_dispatch(const double *sm, const double *xin, int32_t m, int32_t nc,
                                                            int32_t oc, int lane, double *ts) {
-    switch ((nc + 7) >> 3) {
-    case 1: wchunk_tform_dmma<1>(sm, xin, m, nc, oc, lane, ts); break;
-    case 2: wchunk_tform_dmma<2>(sm, xin, m, nc, oc, lane, ts); break;
-    case 3: wchunk_tform_dmma<3>(sm, xin, m, nc, oc, lane, ts); break;
-    case 4: wchunk_tform_dmma<4>(sm, xin, m, nc, oc, lane, ts); break;
-    case 5: wchunk_tform_dmma<5>(sm, xin, m, nc, oc, lane, ts); break;
-    case 6: wchunk_tform_dmma<6>(sm, xin, m, nc, oc, lane, ts); break;
-    case 7: wchunk_tform_dmma<7>(sm, xin, m, nc, oc, lane, ts); break;
-    default: wchunk_tform_dmma<8>(sm, xin, m, nc, oc, lane, ts); break;
+    // at most 4 column tiles (32 columns) per pass: 8 accumulator registers, which keeps the kernel within the 64
+    // registers of 4 CTAs x 256 threads per SM
+    for (int32_t c0 = 0; c0 < nc; c0 += 32) {
+        const int32_t ncp = min(32, nc - c0);
+        const double *smp = sm + c0 * m;
+        switch ((ncp + 7) >> 3) {
+        case 1: wchunk_tform_dmma<1>(smp, xin, m, ncp, oc + c0, lane, ts); break;
+        case 2: wchunk_tform_dmma<2>(smp, xin, m, ncp, oc + c0, lane, ts); break;
+        case 3: wchunk_tform_dmma<3>(smp, xin, m, ncp, oc + c0, lane, ts); break;
+        default: wchunk_tform_dmma<4>(smp, xin, m, ncp, oc + c0, lane, ts); break;
+        }
     }
 }
 
@@ -1170,69 +1172,93 @@ struct WarpEnd {      // CTA-part mode: what a warp's part ended with (shared me
 
 template <class T>
 __host__ __device__ constexpr size_t stream_warp_smem_per_warp() {
-    return (size_t)kWRing + (size_t)kWDSlots * kWDBatch * 32 + 2 * kWSegMax * sizeof(T) + 8 * (kWNB + kWDSlots);
+    return (size_t)kWRing + (size_t)kWDSlots * kWDBatch * 32 + 2 * kWSegMax * sizeof(T) + 8 * (2 * kWNB + kWDSlots);
 }
-// FORM: 0 = the launch holds N-form chunks only, 1 = T-form only, 2 = both (the dead path is compiled out: half the
-// code, which matters for small problems whose first wave also pays the instruction fetch)
-template <class T, bool CONJ, int FORM>
-__device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned char *ring, const int4 *dring,
-                                                 T *xs, T *ts, uint64_t *full, uint64_t *dbar, int32_t q0,
-                                                 int32_t n) {
+// Every work item is served by TWO warps (round 2): a producer warp walks the chunk descriptors and issues the bulk
+// copies as soon as the static ring schedule allows (chunk i needs i - lag chunks consumed: `freed` mbarriers, one
+// arrival per consumed chunk), a consumer warp waits on the `full` barriers and computes. The per-chunk bookkeeping of
+// the two roles (~130 + ~250 instructions, almost all dependent scalar code: ncu shows warps waiting on fixed-latency
+// dependencies and branches, 3 % on memory) now overlaps instead of adding up.
+template <class T>
+__device__ __forceinline__ void wdesc_load_batch(const WarpArgs<T> &a, const int4 *dring, uint64_t *dbar, int32_t q0,
+                                                 int32_t n, int32_t b) {   // one lane
+    const uint32_t cnt = (uint32_t)min(kWDBatch, n - b * kWDBatch);
+    uint64_t *bar = &dbar[b & (kWDSlots - 1)];
+    mbar_arrive_expect_tx(bar, cnt * 32u);
+    bulk_g2s_plain(const_cast<int4 *>(dring) + (b & (kWDSlots - 1)) * kWDBatch * 2, a.chunks + q0 + b * kWDBatch,
+                   cnt * 32u, bar);
+}
+__device__ __forceinline__ WDesc wdesc_at(const int4 *dring, int32_t i) {
+    WDesc d;
+    const int4 *p = dring + (i & (kWDSlots * kWDBatch - 1)) * 2;
+    d.lo = p[0];
+    d.hi = p[1];
+    return d;
+}
+
+template <class T>
+__device__ __forceinline__ void stream_warp_producer(const WarpArgs<T> &a, unsigned char *ring, const int4 *dring,
+                                                     uint64_t *full, uint64_t *dbar, uint64_t *freed, int32_t q0,
+                                                     int32_t n) {
     const int lane = threadIdx.x & 31;
     constexpr int32_t kXVec = (int32_t)(16 / sizeof(T));
     const uint64_t policy = l2_evict_first_policy();
     const int32_t nbatch = (n + kWDBatch - 1) / kWDBatch;
-    auto load_batch = [&](int32_t b) {  // lane 0 only
-        const uint32_t cnt = (uint32_t)min(kWDBatch, n - b * kWDBatch);
-        uint64_t *bar = &dbar[b & (kWDSlots - 1)];
-        mbar_arrive_expect_tx(bar, cnt * 32u);
-        bulk_g2s_plain(const_cast<int4 *>(dring) + (b & (kWDSlots - 1)) * kWDBatch * 2,
-                       a.chunks + q0 + b * kWDBatch, cnt * 32u, bar);
-    };
-    auto desc_at = [&](int32_t i) {
-        WDesc d;
-        const int4 *p = dring + (i & (kWDSlots * kWDBatch - 1)) * 2;
-        d.lo = p[0];
-        d.hi = p[1];
-        return d;
-    };
     if (lane == 0)
-        for (int32_t b = 0; b < kWDSlots && b < nbatch; ++b) load_batch(b);
-    int32_t ii = 0, ibatch = -1, done = 0;
-    // issues every chunk whose ring space is free (warp-uniform; lane 0 drives the TMA, all lanes gather x)
-    auto issue_ready = [&]() {
-        while (ii < n) {
-            const int32_t b = ii / kWDBatch;
-            if (b != ibatch) {
-                mbar_wait(&dbar[b & (kWDSlots - 1)], (uint32_t)((b / kWDSlots) & 1));
-                ibatch = b;
-            }
-            const WDesc d = desc_at(ii);
-            if (ii - d.lag() > done) break;
-            uint64_t *bar = &full[ii & (kWNB - 1)];
-            unsigned char *dst = ring + d.smem_off();
-            const uint32_t bytes = d.bytes();
-            const uint32_t fl = d.flags();
-            const int32_t cnt = (fl & 1u) ? d.m() : d.ncols();
-            const int32_t xr = d.x_ref();
-            const int32_t xa0 = xr & ~(kXVec - 1), xa1 = (xr + cnt + kXVec - 1) & ~(kXVec - 1);
-            const bool xbulk = !(fl & 2u) && xa1 <= a.x_bulk_len;
-            if (lane == 0) {
-                const uint32_t xbytes = xbulk ? (uint32_t)(xa1 - xa0) * (uint32_t)sizeof(T) : 0u;
-                mbar_arrive_expect_tx(bar, bytes + xbytes);
-                bulk_g2s(dst, a.arena + d.src_bytes(), bytes, bar, policy);
-                if (xbulk) bulk_g2s_plain(dst + bytes, a.x.x + xa0, xbytes, bar);   // x is re-read: no evict-first hint
-            }
-            if (!(fl & 2u) && !xbulk) {
-                T *xd = reinterpret_cast<T *>(dst + bytes);
-                if (lane < cnt) cp_async_elem<(int)sizeof(T)>(xd + lane, a.x.ptr(xr + lane));
-                if (lane + 32 < cnt) cp_async_elem<(int)sizeof(T)>(xd + lane + 32, a.x.ptr(xr + lane + 32));
-            }
-            cp_async_mbar_arrive_noinc(bar);
-            ++ii;
+        for (int32_t b = 0; b < kWDSlots && b < nbatch; ++b) wdesc_load_batch(a, dring, dbar, q0, n, b);
+    int32_t ibatch = -1, known = 0;   // known: chunks the consumer is known to have finished
+    for (int32_t ii = 0; ii < n; ++ii) {
+        const int32_t b = ii / kWDBatch;
+        if (b != ibatch) {
+            mbar_wait(&dbar[b & (kWDSlots - 1)], (uint32_t)((b / kWDSlots) & 1));
+            ibatch = b;
         }
-    };
-    issue_ready();
+        const WDesc d = wdesc_at(dring, ii);
+        const int32_t need = ii - d.lag();
+        if (need > known) {   // the ring space of this chunk is free once chunk need - 1 has been consumed
+            mbar_wait(&freed[(need - 1) & (kWNB - 1)], (uint32_t)(((need - 1) / kWNB) & 1));
+            known = need;
+        }
+        uint64_t *bar = &full[ii & (kWNB - 1)];
+        unsigned char *dst = ring + d.smem_off();
+        const uint32_t bytes = d.bytes();
+        const uint32_t fl = d.flags();
+        const int32_t cnt = (fl & 1u) ? d.m() : d.ncols();
+        const int32_t xr = d.x_ref();
+        // x values of the chunk (a contiguous range, unless gathered through the pool by the consumer): ONE bulk copy
+        // of the enclosing 16-byte aligned range when it lies in one array (peer mode: inside one owner's slab),
+        // else one cp.async per entry; either way entry x_ref lands (x_ref mod 16 bytes) behind the chunk
+        const int32_t xa0 = xr & ~(kXVec - 1), xa1 = (xr + cnt + kXVec - 1) & ~(kXVec - 1);
+        bool xbulk = !(fl & 2u) && xa1 <= a.x_bulk_len;
+        const T *xsrc = a.x.x + xa0;
+        if (xbulk && a.x.npeer) {
+            xsrc = a.x.ptr(xa0);
+            xbulk = (xsrc + (xa1 - 1 - xa0)) == a.x.ptr(xa1 - 1);
+        }
+        if (lane == 0) {
+            const uint32_t xbytes = xbulk ? (uint32_t)(xa1 - xa0) * (uint32_t)sizeof(T) : 0u;
+            mbar_arrive_expect_tx(bar, bytes + xbytes);
+            bulk_g2s(dst, a.arena + d.src_bytes(), bytes, bar, policy);
+            if (xbulk) bulk_g2s_plain(dst + bytes, xsrc, xbytes, bar);   // x is re-read: no evict-first hint
+        }
+        if (!(fl & 2u) && !xbulk) {
+            T *xd = reinterpret_cast<T *>(dst + bytes) + (xr - xa0);
+            if (lane < cnt) cp_async_elem<(int)sizeof(T)>(xd + lane, a.x.ptr(xr + lane));
+            if (lane + 32 < cnt) cp_async_elem<(int)sizeof(T)>(xd + lane + 32, a.x.ptr(xr + lane + 32));
+        }
+        cp_async_mbar_arrive_noinc(bar);
+    }
+}
+
+// FORM: 0 = the launch holds N-form chunks only, 1 = T-form only, 2 = both (the dead path is compiled out: half the
+// code, which matters for small problems whose first wave also pays the instruction fetch)
+template <class T, bool CONJ, int FORM>
+__device__ __forceinline__ void stream_warp_consumer(const WarpArgs<T> &a, unsigned char *ring, const int4 *dring,
+                                                     T *xs, T *ts, uint64_t *full, uint64_t *dbar, uint64_t *freed,
+                                                     int32_t q0, int32_t n) {
+    const int lane = threadIdx.x & 31;
+    constexpr int32_t kXVec = (int32_t)(16 / sizeof(T));
+    const int32_t nbatch = (n + kWDBatch - 1) / kWDBatch;
     T acc0 = El<T>::zero(), acc1 = El<T>::zero();
     int32_t cbatch = -1;
     for (int32_t ci = 0; ci < n; ++ci) {
@@ -1240,22 +1266,20 @@ __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned 
         if (b != cbatch) {
             mbar_wait(&dbar[b & (kWDSlots - 1)], (uint32_t)((b / kWDSlots) & 1));
             cbatch = b;
-            // batch b-1 is behind both cursors: its slot takes batch b+3
+            // batch b-1 is behind both cursors (the producer issued its chunks before they were consumed): its slot
+            // takes batch b+3
             if (b >= 1 && b + kWDSlots - 1 < nbatch && lane == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                load_batch(b + kWDSlots - 1);
+                wdesc_load_batch(a, dring, dbar, q0, n, b + kWDSlots - 1);
             }
         }
-        const WDesc d0 = desc_at(ci);
+        const WDesc d0 = wdesc_at(dring, ci);
         const uint32_t fl = d0.flags();
         const int32_t m = d0.m(), nc = d0.ncols();
         const bool tform = FORM == 2 ? (fl & 1u) != 0 : FORM == 1;
         const unsigned char *cbase = ring + d0.smem_off();
         const T *xin = reinterpret_cast<const T *>(cbase + d0.bytes());
-        {   // bulk-fetched x values start at the 16-byte group below x_ref (same test as in issue_ready)
-            const int32_t xr = d0.x_ref(), cnt = (fl & 1u) ? m : nc;
-            if (!(fl & 2u) && ((xr + cnt + kXVec - 1) & ~(kXVec - 1)) <= a.x_bulk_len) xin += xr & (kXVec - 1);
-        }
+        if (!(fl & 2u)) xin += d0.x_ref() & (kXVec - 1);   // see stream_warp_producer
         if (fl & 8u) {  // first chunk of a segment
             acc0 = El<T>::zero();
             acc1 = El<T>::zero();
@@ -1286,7 +1310,10 @@ __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned 
         else
             wchunk_compute<T, CONJ, false>(sm, xin, m, nc, tform, d0.out_col(), lane, acc0, acc1, ts);
         __syncwarp();
-        done = ci + 1;
+        if (lane == 0) {   // the chunk's ring space may be overwritten (by the async proxy) from here on
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&freed[ci & (kWNB - 1)]);
+        }
         if (fl & 16u) {  // last chunk of the segment: write the outputs
             const int32_t L = d0.seg_len();
             const int64_t o = d0.out();
@@ -1316,8 +1343,6 @@ __device__ __forceinline__ void stream_warp_body(const WarpArgs<T> &a, unsigned 
             }
             __syncwarp();
         }
-        if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue_ready();
     }
 }
 
@@ -1326,52 +1351,71 @@ constexpr size_t stream_warp_smem_bytes() {
     return kWWarps * stream_warp_smem_per_warp<T>() + kWWarps * kWSegMax * sizeof(T) + kWWarps * sizeof(WarpEnd);   // + the parts of CTA-part mode
 }
 
+constexpr int kWThreads = 2 * kWWarps * 32;   // consumer warps 0..3, producer warps 4..7 (warp w + 4 feeds warp w)
+
 template <class T, int FORM>
-__global__ void __launch_bounds__(kWWarps * 32) stream_warp_kernel(const WarpArgs<T> a) {
+__global__ void __launch_bounds__(kWThreads, 4) stream_warp_kernel(const WarpArgs<T> a) {
     extern __shared__ __align__(128) unsigned char wsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int32_t nctas = (a.nitems + kWWarps - 1) / kWWarps;
     if ((int32_t)blockIdx.x >= nctas) {   // rows no block touches: y <- beta*y (these CTAs exist in CTA-part mode only)
-        const int32_t i = ((int32_t)blockIdx.x - nctas) * (kWWarps * 32) + (int32_t)threadIdx.x;
+        const int32_t i = ((int32_t)blockIdx.x - nctas) * kWThreads + (int32_t)threadIdx.x;
         if (i < a.nz) {
             const int32_t row = __ldg(a.zrows + i) & 0x7fffffff;
             a.y[row] = a.beta_false ? El<T>::zero() : El<T>::mul(a.beta, a.y[row]);
         }
         return;
     }
-    const int32_t item = blockIdx.x * kWWarps + warp;
-    if (a.x.npeer) {   // every warp is its own pipeline: one arrival per warp
-        if (lane == 0) peer_entry(a.x.sync);
-        __syncwarp();
-    }
+    const bool producer = warp >= kWWarps;
+    const int slot = producer ? warp - kWWarps : warp;
+    const int32_t item = blockIdx.x * kWWarps + slot;
     T *parts = reinterpret_cast<T *>(wsm + kWWarps * stream_warp_smem_per_warp<T>());
     WarpEnd *ends = reinterpret_cast<WarpEnd *>(parts + kWWarps * kWSegMax);
-    if (a.cta_mode && lane == 0) ends[warp].L = -1;      // no part yet
-    __syncwarp();
-    if (item < a.nitems) {
-        unsigned char *base = wsm + warp * stream_warp_smem_per_warp<T>();
-        unsigned char *ring = base;
-        const int4 *dring = reinterpret_cast<const int4 *>(base + kWRing);
-        T *xs = reinterpret_cast<T *>(base + kWRing + kWDSlots * kWDBatch * 32);
-        T *ts = xs + kWSegMax;
-        uint64_t *full = reinterpret_cast<uint64_t *>(ts + kWSegMax);
-        uint64_t *dbar = full + kWNB;
-        if (lane == 0) {
-            for (int i = 0; i < kWNB; ++i) mbar_init(&full[i], 33);  // lane 0's expect_tx + 32 cp.async arrivals
-            for (int i = 0; i < kWDSlots; ++i) mbar_init(&dbar[i], 1);
-            mbar_fence_init();
+    unsigned char *base = wsm + slot * stream_warp_smem_per_warp<T>();
+    unsigned char *ring = base;
+    const int4 *dring = reinterpret_cast<const int4 *>(base + kWRing);
+    T *xs = reinterpret_cast<T *>(base + kWRing + kWDSlots * kWDBatch * 32);
+    T *ts = xs + kWSegMax;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ts + kWSegMax);
+    uint64_t *dbar = full + kWNB;
+    uint64_t *freed = dbar + kWDSlots;
+    if (!producer && lane == 0) {
+        if (a.cta_mode) ends[warp].L = -1;      // no part yet
+        for (int i = 0; i < kWNB; ++i) {
+            mbar_init(&full[i], 33);            // the producer's lane 0 (expect_tx) + its 32 cp.async arrivals
+            mbar_init(&freed[i], 1);            // the consumer's lane 0
         }
-        __syncwarp();
-        const int32_t q0 = __ldg(a.item_ptr + item), q1 = __ldg(a.item_ptr + item + 1);
+        for (int i = 0; i < kWDSlots; ++i) mbar_init(&dbar[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    int32_t q0 = 0, q1 = 0;
+    if (item < a.nitems) {
+        q0 = __ldg(a.item_ptr + item);
+        q1 = __ldg(a.item_ptr + item + 1);
+    }
+    if (producer) {
+        if (q0 < q1) {
+            if (a.x.npeer) {   // no x entry is fetched before every rank has published its slab
+                if (lane == 0) peer_entry(a.x.sync);
+                __syncwarp();
+            }
+            stream_warp_producer<T>(a, ring, dring, full, dbar, freed, q0, q1 - q0);
+        }
+    } else {
+        if (a.x.npeer) {       // pool-gathered x values are read by the consumer itself; every warp arrives at the exit
+            if (lane == 0) peer_entry(a.x.sync);
+            __syncwarp();
+        }
         if (q0 < q1) {
             bool conj_done = false;
             if constexpr (sizeof(T) == 16) {       // conj is the identity for real element types: one instantiation
                 if (a.conj) {
-                    stream_warp_body<T, true, FORM>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0);
+                    stream_warp_consumer<T, true, FORM>(a, ring, dring, xs, ts, full, dbar, freed, q0, q1 - q0);
                     conj_done = true;
                 }
             }
-            if (!conj_done) stream_warp_body<T, false, FORM>(a, ring, dring, xs, ts, full, dbar, q0, q1 - q0);
+            if (!conj_done) stream_warp_consumer<T, false, FORM>(a, ring, dring, xs, ts, full, dbar, freed, q0, q1 - q0);
         }
     }
     if (a.cta_mode) {
@@ -1399,7 +1443,7 @@ __global__ void __launch_bounds__(kWWarps * 32) stream_warp_kernel(const WarpArg
             }
         }
     }
-    if (a.x.npeer) {
+    if (a.x.npeer && !producer) {   // the consumer has seen every chunk's x values land
         __syncwarp();
         if (lane == 0) peer_exit(a.x.sync);
     }
