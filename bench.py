@@ -636,8 +636,12 @@ def run_solver(cx, A, D, SM, own, host_threads, shift=400.0):
     # the set-up of a solve (work vectors; on N > 1 the collective allocation of the peer-mapped search direction) is
     # timed apart from the iterations: one solve cut off after 8 iterations, one to convergence
     solve(1)                      # warm-up: first-use costs (IPC mappings, allocator) stay out of both timed solves
-    _, it8, _, sec8 = solve(8)
-    x, iters, rel, sec = solve(200)
+    # the set-up time varies by tens of milliseconds between solves (collective allocation): best of three for each
+    sec8 = sec = float("inf")
+    for _ in range(3):
+        _, it8, _, t8 = solve(8)
+        x, iters, rel, tf = solve(200)
+        sec8, sec = min(sec8, t8), min(sec, tf)
     sec_it = (sec - sec8) / max(iters - it8, 1) if iters > it8 else sec / max(iters, 1)
     xo = x.clone()
     if world > 1:          # every rank owns a slab of x: assemble the full vector for the oracle check
@@ -657,7 +661,7 @@ def run_solver(cx, A, D, SM, own, host_threads, shift=400.0):
     return {"method": "COCG (bsm_cg%s), diagonal shift %g" % ("_dist" if SM is not None else "", shift), "iterations": iters,
             "relres_reported": rel, "relres_oracle": float(np.sqrt(num / den)), "ms_per_iteration": sec_it * 1e3,
             "solve_ms_end_to_end": sec * 1e3, "update_values_s": round(t_update, 2),
-            "note": "ms_per_iteration = (solve to convergence - solve cut off after 8 iterations) / (iterations - 8): "
+            "note": "ms_per_iteration = (solve to convergence - solve cut off after 8 iterations, best of 3 each) / (iterations - 8): "
                     "multiply + fused vector kernels + dot-product all-reduces + one host synchronisation per 8 iterations"}
 
 
