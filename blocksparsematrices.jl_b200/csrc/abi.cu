@@ -906,6 +906,8 @@ int launch_mul(bsm_matrix *A, int op, const void *alpha, const void *beta, int b
             {
                 bool aligned = (reinterpret_cast<uintptr_t>(w.x.x) & 15) == 0;
                 for (int r = 0; r < w.x.npeer; ++r) aligned = aligned && (reinterpret_cast<uintptr_t>(w.x.peer[r]) & 15) == 0;
+                static const bool no_peer_bulk = std::getenv("BSM_TUNE_NO_XBULK_PEER") && std::atoi(std::getenv("BSM_TUNE_NO_XBULK_PEER"));
+                if (w.x.npeer && no_peer_bulk) aligned = false;   // development knob: per-entry copies of remote x
                 if (aligned) w.x_bulk_len = (int32_t)(HP.in_dim / (16 / (int64_t)sizeof(T)) * (16 / (int64_t)sizeof(T)));
             }
             if (fold_zero_rows) {   // single launch: the rows no block touches are set by extra CTAs of this kernel
