@@ -499,6 +499,14 @@ int bsm_mul_dist(bsm_comm c, bsm_handle h, int op, const void *alpha, const void
 }  // extern "C"
 
 // krylov.cu hook
+// internal (krylov.cu): sets the flags and returns the previous ones
+int bsm_dist_swap_debug_internal(bsm_comm c, int flags) {
+    if (!c) return 0;
+    const int old = c->debug;
+    c->debug = flags;
+    return old;
+}
+
 int bsm_dist_allreduce_sum_f64_internal(bsm_comm c, double *dev_values, int64_t count, void *stream) {
     return bsm_dist_allreduce_sum_f64(c, dev_values, count, stream);
 }

@@ -28,6 +28,7 @@
 
 void bsm_set_error(const std::string &msg);
 int bsm_dist_allreduce_sum_f64_internal(bsm_comm c, double *dev_values, int64_t count, void *stream);
+int bsm_dist_swap_debug_internal(bsm_comm c, int flags);
 
 namespace {
 
@@ -202,12 +203,19 @@ int cg_impl(bsm_comm c, bsm_handle h, const T *b, T *x, const int64_t *cuts, int
     T *r = nullptr, *q = nullptr, *p = nullptr;
     double *scal = nullptr, *part = nullptr, *hist = nullptr;
     void *p_shared = nullptr;
+    // Sharded solve: the multiply's exit barrier (wait until every peer has finished reading this rank's slab of p) is
+    // not needed here — the all-reduce of p.q sits between every multiply and the next update of p, so no rank reaches
+    // that update before all ranks have finished the multiply. Bit 1 of the communicator's flags = no exit wait.
+    const int old_flags = c ? bsm_dist_swap_debug_internal(c, 0) : 0;
+    if (c) bsm_dist_swap_debug_internal(c, old_flags | 2);
     struct Cleanup {
         bsm_comm c;
         T **r, **q, **p;
         double **scal, **part, **hist;
         void **p_shared;
+        int old_flags;
         ~Cleanup() {
+            if (c) bsm_dist_swap_debug_internal(c, old_flags);
             if (*r) cudaFree(*r);
             if (*q) cudaFree(*q);
             if (*scal) cudaFree(*scal);
@@ -218,7 +226,7 @@ int cg_impl(bsm_comm c, bsm_handle h, const T *b, T *x, const int64_t *cuts, int
             else if (*p)
                 cudaFree(*p);
         }
-    } cleanup{c, &r, &q, &p, &scal, &part, &hist, &p_shared};
+    } cleanup{c, &r, &q, &p, &scal, &part, &hist, &p_shared, old_flags};
     K_TRY(cudaMalloc((void **)&r, (size_t)n * sizeof(T)));
     K_TRY(cudaMalloc((void **)&q, (size_t)n * sizeof(T)));
     if (c) {   // the search direction is what the peers read: it lives in a peer-mapped array (collective allocation)

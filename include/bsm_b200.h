@@ -299,7 +299,9 @@ int bsm_dist_set_overlap(bsm_comm c, int on);
  * right-hand side (no staging; 10x slower on 8 GPUs, kept for comparison). */
 int bsm_dist_set_collective(bsm_comm c, int use_broadcasts);
 /* Benchmarking only: bit0 = peer-mode multiplies skip the wait of the entry barrier, bit1 = of the exit barrier
- * (results are then only valid when x does not change between multiplies); bit2 = every arrival waits at system
+ * (results are then only valid when x does not change between multiplies, or when a collective sits between every
+ * multiply and the next write of x — bsm_cg_dist sets this bit itself: the all-reduce of p.q is that collective);
+ * bit2 = every arrival waits at system
  * scope; bit3 = the kernels stamp %globaltimer around the barriers; bit4 = release instead of relaxed signal stores.
  * bsm_dist_debug_read returns (and resets) the sums over the multiplies since the last read: out[0] ns between a
  * kernel's first arrival and the end of its entry wait, out[1] ns first arrival -> last arrival, out[2] ns of the
