@@ -1085,8 +1085,68 @@ __device__ __forceinline__ void wchunk_tform_dmma(const double *__restrict__ sm,
     }
 }
 
+// T-form chunk in Float64 with lanes owning COLUMNS: lane j walks down column j (x[r] is a broadcast), no cross-lane
+// reduction and no tensor-core tile to fill. The 16 lanes of a half-warp read addresses m doubles apart: all 16 banks
+// when m is odd, 2-way conflicts when m = 2 mod 4 — against 4- to 8-way conflicts of the DMMA fragment loads for the
+// same heights. Heights that are multiples of 4 stay on the DMMA path (m = 4 mod 8 is conflict-free there).
+template <bool TWO>
+__device__ __forceinline__ void wchunk_tform_cols32(const double *__restrict__ sm, const double *__restrict__ xin,
+                                                    int32_t m, int32_t nc, int32_t oc, int lane, double *ts) {
+    const bool c0 = lane < nc, c1 = TWO && (lane + 32) < nc;
+    const double *p0 = sm + (c0 ? lane : 0) * m;
+    const double *p1 = sm + (c1 ? lane + 32 : 0) * m;
+    double s0 = 0.0, u0 = 0.0, s1 = 0.0, u1 = 0.0;
+    int32_t r = 0;
+    for (; r + 4 <= m; r += 4) {
+        const double x0 = xin[r], x1 = xin[r + 1], x2 = xin[r + 2], x3 = xin[r + 3];
+        s0 = fma(p0[r], x0, s0);
+        u0 = fma(p0[r + 1], x1, u0);
+        s0 = fma(p0[r + 2], x2, s0);
+        u0 = fma(p0[r + 3], x3, u0);
+        if (TWO) {
+            s1 = fma(p1[r], x0, s1);
+            u1 = fma(p1[r + 1], x1, u1);
+            s1 = fma(p1[r + 2], x2, s1);
+            u1 = fma(p1[r + 3], x3, u1);
+        }
+    }
+    for (; r < m; ++r) {
+        const double x0 = xin[r];
+        s0 = fma(p0[r], x0, s0);
+        if (TWO) s1 = fma(p1[r], x0, s1);
+    }
+    if (c0) ts[oc + lane] += s0 + u0;
+    if (c1) ts[oc + lane + 32] += s1 + u1;
+}
+// at most 16 columns: the two half-warps take the even and the odd rows
+__device__ __forceinline__ void wchunk_tform_cols16(const double *__restrict__ sm, const double *__restrict__ xin,
+                                                    int32_t m, int32_t nc, int32_t oc, int lane, double *ts) {
+    const int j = lane & 15, grp = lane >> 4;
+    const bool cok = j < nc;
+    const double *p = sm + (cok ? j : 0) * m;
+    double s = 0.0, u = 0.0;
+    int32_t r = grp;
+    for (; r + 2 < m; r += 4) {
+        s = fma(p[r], xin[r], s);
+        u = fma(p[r + 2], xin[r + 2], u);
+    }
+    if (r < m) s = fma(p[r], xin[r], s);
+    s += u;
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    if (grp == 0 && cok) ts[oc + j] += s;
+}
+
 __device__ __forceinline__ void wchunk_tform_dmma_dispatch(const double *sm, const double *xin, int32_t m, int32_t nc,
                                                            int32_t oc, int lane, double *ts) {
+    if ((m & 3) != 0 && nc > 8) {   // column stride spreads over the banks: lanes own columns (see above)
+        if (nc > 32)
+            wchunk_tform_cols32<true>(sm, xin, m, nc, oc, lane, ts);
+        else if (nc > 16)
+            wchunk_tform_cols32<false>(sm, xin, m, nc, oc, lane, ts);
+        else
+            wchunk_tform_cols16(sm, xin, m, nc, oc, lane, ts);
+        return;
+    }
     // at most 4 column tiles (32 columns) per pass: 8 accumulator registers, which keeps the kernel within the 64
     // registers of 4 CTAs x 256 threads per SM
     for (int32_t c0 = 0; c0 < nc; c0 += 32) {
