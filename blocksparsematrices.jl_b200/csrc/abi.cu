@@ -370,6 +370,13 @@ int finish_create(bsm_matrix *A, const std::vector<ContribIR> *ir, const bsm_opt
     const int64_t split_div = tune_split ? std::max(1, std::atoi(tune_split)) : 8;
     const int64_t split = std::max<int64_t>(256 << 10, total_bytes / (148 * 2 * split_div));
     if (tune_witems) pp[0].witems_per_slot = pp[1].witems_per_slot = std::max(1, std::atoi(tune_witems));
+    // long segments cut into sub-ranges (1024-row blocks): 2/5 of a resident CTA slot's share per CTA, between
+    // 256 KB and 1 MB — measured on the C4 matrix, transpose(A)*x: 0.151 / 0.141 / 0.130 / 0.147 ms kernel time for
+    // 256 KB / 512 KB / 1 MB / 2 MB per CTA (2886 / 1600 / 820 / 426 CTAs)
+    pp[0].work_target_bytes = pp[1].work_target_bytes =
+        std::min<int64_t>(1 << 20, std::max<int64_t>(256 << 10, total_bytes * 2 / (148 * 2 * 5)));
+    if (const char *tune_wt = std::getenv("BSM_TUNE_WORK_TARGET"))   // development knob: bytes per such CTA
+        pp[0].work_target_bytes = pp[1].work_target_bytes = std::max<int64_t>(64 << 10, std::atoll(tune_wt));
     if (const char *tune_wchunk = std::getenv("BSM_TUNE_WCHUNK"))   // fixed warp-stream chunk payload, 1024 .. 5120 bytes
         pp[0].wchunk_bytes = pp[1].wchunk_bytes = std::min(5120, std::max(1024, std::atoi(tune_wchunk) / 16 * 16));
     std::string err = build_plan(H, ir[0], H.nrows, H.ncols, pp[0], H.plan[0]);
