@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <new>
 #include <string>
@@ -552,7 +553,7 @@ int ensure_piece_maps(bsm_matrix *A, const HostPlan &HP, DevPlan &DP) {
     DP.piece_state = 2;
     if (sizeof(T) > 8 || !encode_tiled_fn()) return 0;
     std::vector<int32_t> cmap(HP.contrib.size(), -1);
-    std::vector<std::pair<int64_t, int64_t>> keys;     // (m, phase in entries)
+    std::map<std::pair<int64_t, int64_t>, int32_t> keys;     // (m, phase in entries) -> map index
     std::vector<CUtensorMap> maps;
     const int64_t cc = kPChunk / (kFMaxRows * (int64_t)sizeof(T));
     for (int64_t i = 0; i < HP.n_fused_slices; ++i) {
@@ -563,9 +564,9 @@ int ensure_piece_maps(bsm_matrix *A, const HostPlan &HP, DevPlan &DP) {
             if (!(sl.r0 > 0 || std::min<int32_t>(sl.r1, cb.out_len) < cb.m)) continue;
             if (cb.m < kFMaxRows || ((int64_t)cb.m * sizeof(T)) % 16 != 0) continue;
             const std::pair<int64_t, int64_t> key(cb.m, cb.off % cb.m);
-            size_t k = 0;
-            while (k < keys.size() && keys[k] != key) ++k;
-            if (k == keys.size()) {
+            auto found = keys.find(key);
+            int32_t k = found == keys.end() ? -1 : found->second;
+            if (k < 0) {
                 if (keys.size() >= kMaxPieceMaps) continue;
                 const int64_t ncol = (A->H.arena_elems - key.second) / cb.m;
                 CUtensorMap tm;
@@ -573,10 +574,11 @@ int ensure_piece_maps(bsm_matrix *A, const HostPlan &HP, DevPlan &DP) {
                                        (unsigned char *)A->arena + key.second * sizeof(T), (uint64_t)cb.m, (uint64_t)ncol,
                                        (uint64_t)cb.m * sizeof(T), kFMaxRows, (uint32_t)cc, CU_TENSOR_MAP_SWIZZLE_NONE))
                     return rc;
-                keys.push_back(key);
+                k = (int32_t)maps.size();
+                keys.emplace(key, k);
                 maps.push_back(tm);
             }
-            cmap[(size_t)c] = (int32_t)k;
+            cmap[(size_t)c] = k;
         }
     }
     if (maps.empty()) return 0;
