@@ -105,12 +105,12 @@ static int64_t wchunk_cols(int64_t m, int64_t n, bool tform, int64_t s, int64_t 
     const int64_t nch = (n + cmax - 1) / cmax;
     int64_t cc = (n + nch - 1) / nch;
     const int64_t c8 = (cc + 7) / 8 * 8, c4 = (cc + 3) / 4 * 4;
+    // rounding UP to whole tiles never adds a chunk; when it would overflow the budget the even split stays as it is
+    // (rounding down would: 36 columns with room for 18 per chunk are 18 + 18, not 16 + 16 + 4)
     if (tform && c8 <= cmax)
         cc = c8;
     else if (c4 <= cmax)
         cc = c4;
-    else
-        cc = cmax >= 4 ? cmax / 4 * 4 : cmax;
     return std::max<int64_t>(cc, 1);
 }
 

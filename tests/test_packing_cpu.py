@@ -475,3 +475,25 @@ def test_small_problem_cta_part_mode_is_single_launch(dtype):
     # the explicit hint restores per-block work items + gather pass (comparison)
     D2 = host_only(A, plan_hints=4)
     assert not np.any(D2.table(L.TAB_WCHUNK, 2)["flags"] & 64) and D2.launch_count("N") == 2
+
+
+def test_warp_stream_chunks_are_as_large_as_the_ring_allows():
+    # the per-chunk cost of stream_warp_kernel is fixed (~1 us of a warp's time), so the chunk COUNT is what a multiply
+    # pays for: chunks of a VBCRS with 8..64-row blocks must average well above the round-1 limit of 4 KB per chunk
+    # wherever the blocks are big enough, and two chunks (with their x values) must always fit the 11 KB ring
+    from bsm_b200 import generators as G
+    V = G.vbcrs_variable(seed=3, n=30000)
+    D = host_only(V)
+    for plan, tform in ((2, 0), (3, 1)):
+        ch = D.table(L.TAB_WCHUNK, plan)
+        assert len(ch) > 0 and np.all((ch["flags"] & 1) == tform)
+        payload = ch["m"].astype(np.int64) * ch["ncols"] * 8
+        cnt = np.where(ch["flags"] & 1, ch["m"], ch["ncols"]).astype(np.int64)
+        foot = ch["bytes16"].astype(np.int64) * 16 + (cnt * 8 + 15) // 16 * 16 + 16
+        assert foot.max() <= 11264 // 2
+        stored = sum(int(b.size) for b in V.blocks) * 8
+        assert payload.sum() == stored
+        # blocks of 8..64 x 8..64 doubles average 11.7 KB: with <= ~5.3 KB per chunk that is ~2.7-2.9 chunks per block
+        # (3.06 when the columns per chunk were rounded DOWN to a multiple of 4: 36 columns became 16 + 16 + 4)
+        assert len(ch) <= 2.9 * len(V.blocks), (len(ch), len(V.blocks))
+        assert payload.mean() >= 4000
